@@ -1,0 +1,632 @@
+// C-ABI of the DeepImpute B200 engine (include/deepimpute_b200.h): handle, device memory, staging and the
+// epoch / step / inference drivers.  All arithmetic is in kernels_simt.cu (DI_MATH_FP32) and kernels_tc.cu
+// (DI_MATH_TF32); there is no host arithmetic and no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "engine.h"
+
+using namespace di;
+
+struct di_handle { Engine e; };
+
+static thread_local std::string g_create_err;
+
+namespace di {
+
+void count_launch(Engine& e, const char*) { ++e.launches; }
+
+// Per-kernel timing: an event pair around every launch on e.stream, recorded without synchronising and resolved
+// at the next host sync (resolve_timers), so the kernels still run back to back while they are being timed.
+static cudaEvent_t pooled_event(Engine& e) {
+    if (!e.event_pool.empty()) { cudaEvent_t ev = e.event_pool.back(); e.event_pool.pop_back(); return ev; }
+    cudaEvent_t ev = nullptr;
+    cudaEventCreate(&ev);
+    return ev;
+}
+KernelTimer::KernelTimer(Engine& e_, const char* n) : e(e_), name(n) {
+    if (!e.profiling) return;
+    a = pooled_event(e); b = pooled_event(e);
+    cudaEventRecord(a, e.stream);
+}
+KernelTimer::~KernelTimer() {
+    if (!a) return;
+    cudaEventRecord(b, e.stream);
+    e.pending_timers.push_back(Engine::PendingTimer{name, a, b});
+}
+void resolve_timers(Engine& e) {
+    for (auto& t : e.pending_timers) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            auto& acc = e.kernel_ms[t.name];
+            acc.first += ms; acc.second += 1;
+        }
+        e.event_pool.push_back(t.a); e.event_pool.push_back(t.b);
+    }
+    e.pending_timers.clear();
+}
+
+}  // namespace di
+
+namespace {
+
+#define DI_CUDA(call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t err__ = (call);                                                                       \
+        if (err__ != cudaSuccess) {                                                                       \
+            char buf__[512];                                                                              \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__),      \
+                     __FILE__, __LINE__);                                                                 \
+            e.err = buf__;                                                                                \
+            return err__ == cudaErrorMemoryAllocation ? DI_ERR_OOM : DI_ERR_CUDA;                         \
+        }                                                                                                 \
+    } while (0)
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+template <typename T>
+int dev_alloc(Engine& e, T** p, int64_t count, bool zero = true) {
+    *p = nullptr;
+    if (count <= 0) return DI_OK;
+    DI_CUDA(cudaMalloc((void**)p, (size_t)count * sizeof(T)));
+    if (zero) DI_CUDA(cudaMemsetAsync(*p, 0, (size_t)count * sizeof(T), e.stream));
+    return DI_OK;
+}
+template <typename T>
+void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+int fail(Engine& e, int code, const char* msg) { e.err = msg; return code; }
+
+AdamParams adam_for_step(const Engine& e, int64_t step) {
+    // Keras/TF: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), t = 1 for the first step
+    const double t = (double)(step + 1);
+    const double b1 = (double)e.cfg.beta1;   // cfg carries float32 values
+    const double b2 = (double)e.cfg.beta2;
+    AdamParams a;
+    a.lr_t = (float)((double)e.cfg.learning_rate * std::sqrt(1.0 - std::pow(b2, t)) / (1.0 - std::pow(b1, t)));
+    a.one_minus_b1 = 1.0f - e.cfg.beta1;
+    a.one_minus_b2 = 1.0f - e.cfg.beta2;
+    a.eps = e.cfg.epsilon;
+    return a;
+}
+
+int sync_check(Engine& e) {
+    DI_CUDA(cudaStreamSynchronize(e.stream));
+    DI_CUDA(cudaGetLastError());
+    if (!e.pending_timers.empty()) resolve_timers(e);
+    return DI_OK;
+}
+
+void free_split(Engine& e) {
+    dev_free(e.d_train_rows); dev_free(e.d_test_rows); dev_free(e.d_perm);
+    dev_free(e.Xtr); dev_free(e.Ytr); dev_free(e.Xte); dev_free(e.Yte);
+    e.n_train = e.n_test = e.n_train_pad = e.n_test_pad = 0;
+}
+
+int run_step(Engine& e, const float* X, const float* Y, int64_t row0, int n_valid, int64_t step, int which_x) {
+    StepArgs a;
+    a.X = X; a.Y = Y; a.ldx = e.PT; a.ldy = (int64_t)e.S * e.Op; a.row0 = row0; a.n_valid = n_valid;
+    a.step = (uint32_t)step; a.adam = adam_for_step(e, step);
+    if (e.cfg.math_mode == DI_MATH_TF32) tc_train_step(e, a, which_x);
+    else simt_train_step(e, a);
+    e.adam_t = step + 1;
+    return DI_OK;
+}
+
+// forward over rows [row0, row0+rows) of a resident packed matrix; rows is a multiple of 128
+void run_forward(Engine& e, int which_x, const float* X, const float* Y, int64_t row0, int64_t rows,
+                 int64_t n_valid, float* out, int64_t ld_out) {
+    if (e.cfg.math_mode == DI_MATH_TF32) {
+        tc_forward(e, which_x, row0, rows, n_valid, Y != nullptr, out, ld_out);
+    } else {
+        simt_forward(e, X + row0 * e.PT, e.PT, rows, n_valid, e.Hchunk,
+                     Y ? Y + row0 * (int64_t)e.S * e.Op : nullptr, (int64_t)e.S * e.Op, out, ld_out);
+    }
+}
+
+int validation_pass(Engine& e) {
+    DI_CUDA(cudaMemsetAsync(e.d_loss + 1, 0, sizeof(double), e.stream));
+    for (int64_t r0 = 0; r0 < e.n_test_pad; r0 += e.chunk_rows) {
+        const int64_t rows = std::min(e.chunk_rows, e.n_test_pad - r0);
+        const int64_t valid = std::max<int64_t>(0, std::min(rows, e.n_test - r0));
+        run_forward(e, 2, e.Xte, e.Yte, r0, rows, valid, nullptr, 0);
+    }
+    return DI_OK;
+}
+
+int read_losses(Engine& e, double out[2]) {
+    DI_CUDA(cudaMemcpyAsync(out, e.d_loss, 2 * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    return sync_check(e);
+}
+
+}  // namespace
+
+extern "C" {
+
+int di_version(void) { return 100; }
+
+int di_math_mode_available(int32_t math_mode) {
+    if (math_mode == DI_MATH_FP32) return 1;
+    if (math_mode == DI_MATH_TF32) return tc_available() ? 1 : 0;
+    return 0;
+}
+
+const char* di_last_error(const di_handle* h) { return h ? h->e.err.c_str() : g_create_err.c_str(); }
+
+int di_create(di_handle** out, const di_config* cfg, const int32_t* n_pred) {
+    if (!out || !cfg || !n_pred) { g_create_err = "null argument"; return DI_ERR_ARG; }
+    *out = nullptr;
+    if (cfg->n_subnets <= 0 || cfg->hidden <= 0 || cfg->sub_outputdim <= 0 || cfg->batch_size <= 0 ||
+        cfg->dropout_rate < 0.f || cfg->dropout_rate >= 1.f ||
+        (cfg->math_mode != DI_MATH_FP32 && cfg->math_mode != DI_MATH_TF32)) {
+        g_create_err = "invalid di_config"; return DI_ERR_ARG;
+    }
+    for (int s = 0; s < cfg->n_subnets; ++s)
+        if (n_pred[s] <= 0) { g_create_err = "n_pred must be positive"; return DI_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(ce);
+        return DI_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "device ordinal out of range"; return DI_ERR_ARG; }
+    di_handle* h = new (std::nothrow) di_handle();
+    if (!h) { g_create_err = "host allocation failed"; return DI_ERR_OOM; }
+    Engine& e = h->e;
+    e.cfg = *cfg;
+    e.S = cfg->n_subnets; e.H = cfg->hidden; e.O = cfg->sub_outputdim; e.B = cfg->batch_size;
+    e.Hp = round_up(e.H, 32); e.Op = round_up(e.O, 32);
+    e.P.assign(n_pred, n_pred + e.S);
+    e.Pp.resize(e.S); e.coff.resize(e.S);
+    int64_t off = 0;
+    for (int s = 0; s < e.S; ++s) {
+        e.Pp[s] = round_up(e.P[s], 32);
+        e.coff[s] = off; off += e.Pp[s];
+        e.maxPp = std::max(e.maxPp, e.Pp[s]);
+    }
+    e.PT = off;
+
+    auto body = [&]() -> int {
+        DI_CUDA(cudaSetDevice(cfg->device));
+        DI_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+        DI_CUDA(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
+        DI_CUDA(cudaEventCreate(&e.ev0)); DI_CUDA(cudaEventCreate(&e.ev1));
+        DI_CUDA(cudaEventCreate(&e.ev_t0)); DI_CUDA(cudaEventCreate(&e.ev_t1));
+        std::vector<SubnetDesc> desc(e.S);
+        for (int s = 0; s < e.S; ++s) desc[s] = SubnetDesc{e.coff[s], e.P[s], e.Pp[s], s, 0};
+        e.gid.resize(e.S);
+        for (int s = 0; s < e.S; ++s) e.gid[s] = s;
+        int rc;
+        if ((rc = dev_alloc(e, &e.d_desc, e.S))) return rc;
+        DI_CUDA(cudaMemcpyAsync(e.d_desc, desc.data(), sizeof(SubnetDesc) * e.S, cudaMemcpyHostToDevice, e.stream));
+        const int64_t n1 = e.PT * e.Hp, nb1 = (int64_t)e.S * e.Hp, n2 = (int64_t)e.S * e.Hp * e.Op, nb2 = (int64_t)e.S * e.Op;
+        float** w1[] = {&e.W1, &e.mW1, &e.vW1}; float** bb1[] = {&e.b1, &e.mb1, &e.vb1};
+        float** w2[] = {&e.W2, &e.mW2, &e.vW2}; float** bb2[] = {&e.b2, &e.mb2, &e.vb2};
+        for (int i = 0; i < 3; ++i) {
+            if ((rc = dev_alloc(e, w1[i], n1))) return rc;
+            if ((rc = dev_alloc(e, bb1[i], nb1))) return rc;
+            if ((rc = dev_alloc(e, w2[i], n2))) return rc;
+            if ((rc = dev_alloc(e, bb2[i], nb2))) return rc;
+        }
+        if ((rc = dev_alloc(e, &e.d_pred_cols, e.PT))) return rc;
+        if ((rc = dev_alloc(e, &e.d_targ_cols, nb2))) return rc;
+        if ((rc = dev_alloc(e, &e.Xstep, (int64_t)e.B * e.PT))) return rc;
+        if ((rc = dev_alloc(e, &e.Ystep, (int64_t)e.B * nb2))) return rc;
+        if ((rc = dev_alloc(e, &e.d_step_rows, e.B))) return rc;
+        if ((rc = dev_alloc(e, &e.Hact, (int64_t)e.B * nb1))) return rc;
+        if ((rc = dev_alloc(e, &e.DZ2, (int64_t)e.B * nb2))) return rc;
+        if ((rc = dev_alloc(e, &e.DZ1, (int64_t)e.B * nb1))) return rc;
+        if ((rc = dev_alloc(e, &e.d_loss, 2))) return rc;
+        // inference chunk: keep Xchunk + Hchunk + Ochunk around 1.5 GB
+        const int64_t per_row = (e.PT + nb1 + 2 * nb2) * (int64_t)sizeof(float);
+        int64_t cr = (int64_t)(1536ll << 20) / std::max<int64_t>(per_row, 1);
+        cr = std::max<int64_t>(128, std::min<int64_t>(cr / 128 * 128, 16384));
+        e.chunk_rows = cr;
+        if ((rc = dev_alloc(e, &e.Xchunk, cr * e.PT))) return rc;
+        if ((rc = dev_alloc(e, &e.Hchunk, cr * nb1))) return rc;
+        if ((rc = dev_alloc(e, &e.Ochunk, cr * nb2))) return rc;
+        if ((rc = dev_alloc(e, &e.OchunkB, cr * nb2))) return rc;
+        e.Ochunk2[0] = e.Ochunk; e.Ochunk2[1] = e.OchunkB;
+        if ((rc = dev_alloc(e, &e.d_chunk_rows, cr))) return rc;
+        for (int i = 0; i < 2; ++i) {
+            DI_CUDA(cudaMallocHost((void**)&e.h_pinned[i], (size_t)cr * e.S * e.O * sizeof(float)));
+            DI_CUDA(cudaEventCreateWithFlags(&e.ev_pinned[i], cudaEventDisableTiming));
+            DI_CUDA(cudaEventCreateWithFlags(&e.ev_fwd[i], cudaEventDisableTiming));
+        }
+        if (cfg->math_mode == DI_MATH_TF32 && !tc_init(e)) return DI_ERR_CUDA;
+        return sync_check(e);
+    };
+    int rc = body();
+    if (rc != DI_OK) { g_create_err = e.err; di_destroy(h); return rc; }
+    *out = h;
+    return DI_OK;
+}
+
+void di_destroy(di_handle* h) {
+    if (!h) return;
+    Engine& e = h->e;
+    cudaSetDevice(e.cfg.device);
+    if (e.stream) cudaStreamSynchronize(e.stream);
+    tc_destroy(e);
+    free_split(e);
+    dev_free(e.d_desc); dev_free(e.d_norm); dev_free(e.d_pred_cols); dev_free(e.d_targ_cols);
+    float** all[] = {&e.W1, &e.mW1, &e.vW1, &e.b1, &e.mb1, &e.vb1, &e.W2, &e.mW2, &e.vW2, &e.b2, &e.mb2, &e.vb2,
+                     &e.Xstep, &e.Ystep, &e.Hact, &e.DZ2, &e.DZ1, &e.Xchunk, &e.Hchunk, &e.Ochunk, &e.OchunkB};
+    for (float** p : all) dev_free(*p);
+    dev_free(e.d_step_rows); dev_free(e.d_chunk_rows); dev_free(e.d_loss);
+    resolve_timers(e);
+    for (cudaEvent_t ev : e.event_pool) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        if (e.h_pinned[i]) cudaFreeHost(e.h_pinned[i]);
+        if (e.ev_pinned[i]) cudaEventDestroy(e.ev_pinned[i]);
+        if (e.ev_fwd[i]) cudaEventDestroy(e.ev_fwd[i]);
+    }
+    if (e.ev0) cudaEventDestroy(e.ev0);
+    if (e.ev1) cudaEventDestroy(e.ev1);
+    if (e.ev_t0) cudaEventDestroy(e.ev_t0);
+    if (e.ev_t1) cudaEventDestroy(e.ev_t1);
+    if (e.stream) cudaStreamDestroy(e.stream);
+    if (e.copy_stream) cudaStreamDestroy(e.copy_stream);
+    delete h;
+}
+
+int di_set_subnet_ids(di_handle* h, const int32_t* ids) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!ids) return fail(e, DI_ERR_ARG, "di_set_subnet_ids: null argument");
+    for (int s = 0; s < e.S; ++s) if (ids[s] < 0) return fail(e, DI_ERR_ARG, "di_set_subnet_ids: negative id");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    std::vector<SubnetDesc> desc(e.S);
+    for (int s = 0; s < e.S; ++s) { e.gid[s] = ids[s]; desc[s] = SubnetDesc{e.coff[s], e.P[s], e.Pp[s], ids[s], 0}; }
+    DI_CUDA(cudaMemcpyAsync(e.d_desc, desc.data(), sizeof(SubnetDesc) * e.S, cudaMemcpyHostToDevice, e.stream));
+    return sync_check(e);
+}
+
+int di_upload_matrix(di_handle* h, const float* norm, int64_t n_cells, int64_t n_genes) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!norm || n_cells <= 0 || n_genes <= 0) return fail(e, DI_ERR_ARG, "di_upload_matrix: bad arguments");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    if (n_cells != e.N || n_genes != e.G) {
+        DI_CUDA(cudaStreamSynchronize(e.stream));
+        dev_free(e.d_norm);
+        free_split(e);
+        e.N = e.G = 0;
+        int rc = dev_alloc(e, &e.d_norm, n_cells * n_genes, false);
+        if (rc) return rc;
+        e.N = n_cells; e.G = n_genes;
+    }
+    DI_CUDA(cudaMemcpyAsync(e.d_norm, norm, (size_t)n_cells * n_genes * sizeof(float), cudaMemcpyHostToDevice, e.stream));
+    return sync_check(e);
+}
+
+int di_set_partition(di_handle* h, const int32_t* pred_idx, const int64_t* pred_off, const int32_t* targ_idx) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!pred_idx || !pred_off || !targ_idx) return fail(e, DI_ERR_ARG, "di_set_partition: null argument");
+    if (!e.d_norm) return fail(e, DI_ERR_ARG, "di_set_partition: call di_upload_matrix first");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    std::vector<int32_t> pc((size_t)e.PT, -1), tc((size_t)e.S * e.Op, -1);
+    for (int s = 0; s < e.S; ++s) {
+        if (pred_off[s + 1] - pred_off[s] != e.P[s]) return fail(e, DI_ERR_ARG, "di_set_partition: pred_off does not match n_pred");
+        for (int j = 0; j < e.P[s]; ++j) {
+            const int32_t c = pred_idx[pred_off[s] + j];
+            if (c < 0 || c >= e.G) return fail(e, DI_ERR_ARG, "di_set_partition: predictor column out of range");
+            pc[(size_t)e.coff[s] + j] = c;
+        }
+        for (int o = 0; o < e.O; ++o) {
+            const int32_t c = targ_idx[(size_t)s * e.O + o];
+            if (c < 0 || c >= e.G) return fail(e, DI_ERR_ARG, "di_set_partition: target column out of range");
+            tc[(size_t)s * e.Op + o] = c;
+        }
+    }
+    DI_CUDA(cudaMemcpyAsync(e.d_pred_cols, pc.data(), pc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
+    DI_CUDA(cudaMemcpyAsync(e.d_targ_cols, tc.data(), tc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
+    int rc = sync_check(e);
+    e.have_partition = rc == DI_OK;
+    // a new partition invalidates staged train/test matrices
+    if (e.n_train || e.n_test) free_split(e);
+    return rc;
+}
+
+int di_set_split(di_handle* h, const int32_t* train_rows, int64_t n_train, const int32_t* test_rows, int64_t n_test) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!e.have_partition) return fail(e, DI_ERR_ARG, "di_set_split: call di_set_partition first");
+    if (n_train < 0 || n_test < 0 || (n_train && !train_rows) || (n_test && !test_rows))
+        return fail(e, DI_ERR_ARG, "di_set_split: bad arguments");
+    for (int64_t i = 0; i < n_train; ++i) if (train_rows[i] < 0 || train_rows[i] >= e.N) return fail(e, DI_ERR_ARG, "di_set_split: train row out of range");
+    for (int64_t i = 0; i < n_test; ++i) if (test_rows[i] < 0 || test_rows[i] >= e.N) return fail(e, DI_ERR_ARG, "di_set_split: test row out of range");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    DI_CUDA(cudaStreamSynchronize(e.stream));
+    free_split(e);
+    const int64_t ldy = (int64_t)e.S * e.Op;
+    e.n_train = n_train; e.n_test = n_test;
+    e.n_train_pad = round_up64(std::max<int64_t>(n_train, 1), e.B);
+    e.n_test_pad = round_up64(std::max<int64_t>(n_test, 1), 128);
+    int rc;
+    if ((rc = dev_alloc(e, &e.d_train_rows, std::max<int64_t>(n_train, 1)))) return rc;
+    if ((rc = dev_alloc(e, &e.d_perm, std::max<int64_t>(n_train, 1)))) return rc;
+    if ((rc = dev_alloc(e, &e.d_test_rows, std::max<int64_t>(n_test, 1)))) return rc;
+    if ((rc = dev_alloc(e, &e.Xtr, e.n_train_pad * e.PT, false))) return rc;
+    if ((rc = dev_alloc(e, &e.Ytr, e.n_train_pad * ldy, false))) return rc;
+    if ((rc = dev_alloc(e, &e.Xte, e.n_test_pad * e.PT, false))) return rc;
+    if ((rc = dev_alloc(e, &e.Yte, e.n_test_pad * ldy, false))) return rc;
+    if (n_train) DI_CUDA(cudaMemcpyAsync(e.d_train_rows, train_rows, n_train * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
+    if (n_test) DI_CUDA(cudaMemcpyAsync(e.d_test_rows, test_rows, n_test * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
+    // held-out matrices are staged once; training matrices are re-gathered in shuffled order every epoch
+    launch_gather(e, e.d_test_rows, nullptr, 0, e.n_test_pad, n_test, e.d_pred_cols, e.PT, e.Xte);
+    launch_gather(e, e.d_test_rows, nullptr, 0, e.n_test_pad, n_test, e.d_targ_cols, ldy, e.Yte);
+    if (e.cfg.math_mode == DI_MATH_TF32 && !tc_rebind(e)) return DI_ERR_CUDA;
+    return sync_check(e);
+}
+
+static int weights_xfer(di_handle* h, int32_t s, float* W1, float* b1, float* W2, float* b2, int which, bool to_device) {
+    // which: 0 = weights, 1 = first moments, 2 = second moments
+    Engine& e = h->e;
+    if (s < 0 || s >= e.S) return fail(e, DI_ERR_ARG, "sub-network index out of range");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    float* dW1 = (which == 0 ? e.W1 : which == 1 ? e.mW1 : e.vW1) + e.coff[s] * e.Hp;
+    float* db1 = (which == 0 ? e.b1 : which == 1 ? e.mb1 : e.vb1) + (int64_t)s * e.Hp;
+    float* dW2 = (which == 0 ? e.W2 : which == 1 ? e.mW2 : e.vW2) + (int64_t)s * e.Hp * e.Op;
+    float* db2 = (which == 0 ? e.b2 : which == 1 ? e.mb2 : e.vb2) + (int64_t)s * e.Op;
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    auto copy2d = [&](float* dev, int64_t dpitch, float* host, int64_t rows, int64_t cols) -> cudaError_t {
+        if (!host) return cudaSuccess;
+        return to_device
+            ? cudaMemcpy2DAsync(dev, dpitch * sizeof(float), host, cols * sizeof(float), cols * sizeof(float), rows, kind, e.stream)
+            : cudaMemcpy2DAsync(host, cols * sizeof(float), dev, dpitch * sizeof(float), cols * sizeof(float), rows, kind, e.stream);
+    };
+    DI_CUDA(copy2d(dW1, e.Hp, W1, e.P[s], e.H));
+    DI_CUDA(copy2d(db1, e.Hp, b1, 1, e.H));
+    DI_CUDA(copy2d(dW2, e.Op, W2, e.H, e.O));
+    DI_CUDA(copy2d(db2, e.Op, b2, 1, e.O));
+    return sync_check(e);
+}
+
+int di_set_weights(di_handle* h, int32_t s, const float* W1, const float* b1, const float* W2, const float* b2) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!W1 || !b1 || !W2 || !b2) return fail(e, DI_ERR_ARG, "di_set_weights: null argument");
+    if (s < 0 || s >= e.S) return fail(e, DI_ERR_ARG, "sub-network index out of range");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    // zero the padded blocks (weights and both moments) before copying the real entries in
+    float* w1[] = {e.W1, e.mW1, e.vW1}; float* bb1[] = {e.b1, e.mb1, e.vb1};
+    float* w2[] = {e.W2, e.mW2, e.vW2}; float* bb2[] = {e.b2, e.mb2, e.vb2};
+    for (int i = 0; i < 3; ++i) {
+        DI_CUDA(cudaMemsetAsync(w1[i] + e.coff[s] * e.Hp, 0, (size_t)e.Pp[s] * e.Hp * sizeof(float), e.stream));
+        DI_CUDA(cudaMemsetAsync(bb1[i] + (int64_t)s * e.Hp, 0, (size_t)e.Hp * sizeof(float), e.stream));
+        DI_CUDA(cudaMemsetAsync(w2[i] + (int64_t)s * e.Hp * e.Op, 0, (size_t)e.Hp * e.Op * sizeof(float), e.stream));
+        DI_CUDA(cudaMemsetAsync(bb2[i] + (int64_t)s * e.Op, 0, (size_t)e.Op * sizeof(float), e.stream));
+    }
+    e.adam_t = 0;
+    return weights_xfer(h, s, const_cast<float*>(W1), const_cast<float*>(b1), const_cast<float*>(W2),
+                        const_cast<float*>(b2), 0, true);
+}
+
+int di_get_weights(di_handle* h, int32_t s, float* W1, float* b1, float* W2, float* b2) {
+    if (!h) return DI_ERR_ARG;
+    return weights_xfer(h, s, W1, b1, W2, b2, 0, false);
+}
+
+int di_get_adam_state(di_handle* h, int32_t s, float* mW1, float* vW1, float* mb1, float* vb1,
+                      float* mW2, float* vW2, float* mb2, float* vb2, int64_t* t) {
+    if (!h) return DI_ERR_ARG;
+    int rc = weights_xfer(h, s, mW1, mb1, mW2, mb2, 1, false);
+    if (rc) return rc;
+    rc = weights_xfer(h, s, vW1, vb1, vW2, vb2, 2, false);
+    if (t) *t = h->e.adam_t;
+    return rc;
+}
+
+int di_train_step(di_handle* h, const int32_t* rows, int32_t nrows, int64_t step, float* loss_out) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!e.have_partition) return fail(e, DI_ERR_ARG, "di_train_step: no data (di_upload_matrix + di_set_partition)");
+    if (!rows || nrows <= 0 || nrows > e.B || step < 0) return fail(e, DI_ERR_ARG, "di_train_step: need 1..B rows");
+    for (int i = 0; i < nrows; ++i) if (rows[i] < 0 || rows[i] >= e.N) return fail(e, DI_ERR_ARG, "di_train_step: row out of range");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    DI_CUDA(cudaMemcpyAsync(e.d_step_rows, rows, nrows * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
+    DI_CUDA(cudaEventRecord(e.ev0, e.stream));
+    DI_CUDA(cudaMemsetAsync(e.d_loss, 0, sizeof(double), e.stream));
+    launch_gather(e, e.d_step_rows, nullptr, 0, e.B, nrows, e.d_pred_cols, e.PT, e.Xstep);
+    launch_gather(e, e.d_step_rows, nullptr, 0, e.B, nrows, e.d_targ_cols, (int64_t)e.S * e.Op, e.Ystep);
+    int rc = run_step(e, e.Xstep, e.Ystep, 0, nrows, step, 1);
+    if (rc) return rc;
+    DI_CUDA(cudaEventRecord(e.ev1, e.stream));
+    double l[2];
+    if ((rc = read_losses(e, l))) return rc;
+    DI_CUDA(cudaEventElapsedTime(&e.last_ms, e.ev0, e.ev1));
+    if (loss_out) *loss_out = (float)(l[0] / ((double)nrows * e.O));
+    return std::isfinite(l[0]) ? DI_OK : fail(e, DI_ERR_NUMERIC, "non-finite training loss");
+}
+
+int di_validation_loss(di_handle* h, float* val_loss_out) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!e.Xte) return fail(e, DI_ERR_ARG, "di_validation_loss: call di_set_split first");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    int rc = validation_pass(e);
+    if (rc) return rc;
+    double l[2];
+    if ((rc = read_losses(e, l))) return rc;
+    if (val_loss_out) *val_loss_out = e.n_test ? (float)(l[1] / ((double)e.n_test * e.O)) : 0.f;
+    return DI_OK;
+}
+
+int di_train_epoch(di_handle* h, const int32_t* perm, int64_t first_step, float* loss_out, float* val_loss_out) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!e.Xtr || e.n_train <= 0) return fail(e, DI_ERR_ARG, "di_train_epoch: call di_set_split first");
+    if (!perm || first_step < 0) return fail(e, DI_ERR_ARG, "di_train_epoch: bad arguments");
+    for (int64_t i = 0; i < e.n_train; ++i) if (perm[i] < 0 || perm[i] >= e.n_train) return fail(e, DI_ERR_ARG, "di_train_epoch: perm out of range");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    const int64_t ldy = (int64_t)e.S * e.Op;
+    DI_CUDA(cudaMemcpyAsync(e.d_perm, perm, e.n_train * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
+    DI_CUDA(cudaEventRecord(e.ev0, e.stream));
+    DI_CUDA(cudaMemsetAsync(e.d_loss, 0, 2 * sizeof(double), e.stream));
+    // stage this epoch's visiting order: batch i is rows [i*B, (i+1)*B) of Xtr / Ytr
+    launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_pred_cols, e.PT, e.Xtr);
+    launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_targ_cols, ldy, e.Ytr);
+    int64_t step = first_step;
+    for (int64_t r0 = 0; r0 < e.n_train; r0 += e.B, ++step) {
+        const int n_valid = (int)std::min<int64_t>(e.B, e.n_train - r0);
+        int rc = run_step(e, e.Xtr, e.Ytr, r0, n_valid, step, 0);
+        if (rc) return rc;
+    }
+    int rc = validation_pass(e);
+    if (rc) return rc;
+    DI_CUDA(cudaEventRecord(e.ev1, e.stream));
+    double l[2];
+    if ((rc = read_losses(e, l))) return rc;
+    DI_CUDA(cudaEventElapsedTime(&e.last_ms, e.ev0, e.ev1));
+    // Keras `loss`: sum_batches(L_batch * n_batch) / n_train with L_batch = raw / (n_batch * O)
+    if (loss_out) *loss_out = (float)(l[0] / ((double)e.n_train * e.O));
+    if (val_loss_out) *val_loss_out = e.n_test ? (float)(l[1] / ((double)e.n_test * e.O)) : 0.f;
+    return std::isfinite(l[0]) ? DI_OK : fail(e, DI_ERR_NUMERIC, "non-finite training loss");
+}
+
+static int predict_impl(di_handle* h, const int32_t* rows, int64_t n, float* host_out, float* d_out, int64_t ld_out) {
+    Engine& e = h->e;
+    if (!e.have_partition) return fail(e, DI_ERR_ARG, "di_predict: no data (di_upload_matrix + di_set_partition)");
+    if (n < 0 || (!rows && n > e.N)) return fail(e, DI_ERR_ARG, "di_predict: bad row count");
+    if (n == 0) return DI_OK;
+    if (rows) for (int64_t i = 0; i < n; ++i) if (rows[i] < 0 || rows[i] >= e.N) return fail(e, DI_ERR_ARG, "di_predict: row out of range");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    const int64_t SO = (int64_t)e.S * e.O;
+    // a page-locked caller buffer takes the DMA directly; a pageable one is fed through two pinned staging buffers
+    bool direct = false;
+    if (host_out) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, host_out) == cudaSuccess && attr.type == cudaMemoryTypeHost) direct = true;
+        cudaGetLastError();
+    }
+    DI_CUDA(cudaEventRecord(e.ev0, e.stream));
+    int buf = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += e.chunk_rows, buf ^= 1) {
+        const int64_t valid = std::min(e.chunk_rows, n - r0);
+        const int64_t rows_pad = round_up64(valid, 128);
+        if (rows) DI_CUDA(cudaMemcpyAsync(e.d_chunk_rows, rows + r0, valid * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
+        launch_gather(e, rows ? e.d_chunk_rows : nullptr, nullptr, r0, rows_pad, valid, e.d_pred_cols, e.PT, e.Xchunk);
+        if (d_out) {
+            run_forward(e, 3, e.Xchunk, nullptr, 0, rows_pad, valid, d_out + r0 * ld_out, ld_out);
+        } else if (direct) {
+            float* o = e.Ochunk2[buf];
+            // the copy of chunk i-2 out of this buffer must have finished before chunk i overwrites it
+            DI_CUDA(cudaStreamWaitEvent(e.stream, e.ev_pinned[buf], 0));
+            run_forward(e, 3, e.Xchunk, nullptr, 0, rows_pad, valid, o, SO);
+            DI_CUDA(cudaEventRecord(e.ev_fwd[buf], e.stream));
+            DI_CUDA(cudaStreamWaitEvent(e.copy_stream, e.ev_fwd[buf], 0));
+            DI_CUDA(cudaMemcpyAsync(host_out + r0 * SO, o, (size_t)valid * SO * sizeof(float), cudaMemcpyDeviceToHost, e.copy_stream));
+            DI_CUDA(cudaEventRecord(e.ev_pinned[buf], e.copy_stream));
+        } else {
+            run_forward(e, 3, e.Xchunk, nullptr, 0, rows_pad, valid, e.Ochunk, SO);
+            // D2H through two pinned buffers so the next chunk's kernels overlap the host-side copy-out
+            DI_CUDA(cudaEventSynchronize(e.ev_pinned[buf]));
+            DI_CUDA(cudaMemcpyAsync(e.h_pinned[buf], e.Ochunk, (size_t)valid * SO * sizeof(float), cudaMemcpyDeviceToHost, e.stream));
+            DI_CUDA(cudaEventRecord(e.ev_pinned[buf], e.stream));
+            if (r0 > 0) {
+                const int prev = buf ^ 1;
+                const int64_t pr0 = r0 - e.chunk_rows;
+                DI_CUDA(cudaEventSynchronize(e.ev_pinned[prev]));
+                memcpy(host_out + pr0 * SO, e.h_pinned[prev], (size_t)e.chunk_rows * SO * sizeof(float));
+            }
+        }
+    }
+    if (direct) {   // the timed region ends when the last copy has landed
+        DI_CUDA(cudaStreamWaitEvent(e.stream, e.ev_pinned[0], 0));
+        DI_CUDA(cudaStreamWaitEvent(e.stream, e.ev_pinned[1], 0));
+    }
+    DI_CUDA(cudaEventRecord(e.ev1, e.stream));
+    int rc = sync_check(e);
+    if (rc) return rc;
+    if (!d_out && !direct) {
+        const int64_t last0 = (n - 1) / e.chunk_rows * e.chunk_rows;
+        const int last_buf = (int)((last0 / e.chunk_rows) & 1);
+        memcpy(host_out + last0 * SO, e.h_pinned[last_buf], (size_t)(n - last0) * SO * sizeof(float));
+    }
+    DI_CUDA(cudaEventElapsedTime(&e.last_ms, e.ev0, e.ev1));
+    return DI_OK;
+}
+
+int di_predict(di_handle* h, const int32_t* rows, int64_t n, float* out) {
+    if (!h) return DI_ERR_ARG;
+    if (!out && n > 0) return fail(h->e, DI_ERR_ARG, "di_predict: null output");
+    return predict_impl(h, rows, n, out, nullptr, 0);
+}
+
+int di_predict_device(di_handle* h, const int32_t* rows, int64_t n, float* d_out, int64_t ld_out) {
+    if (!h) return DI_ERR_ARG;
+    if ((!d_out && n > 0) || ld_out < (int64_t)h->e.S * h->e.O) return fail(h->e, DI_ERR_ARG, "di_predict_device: bad output");
+    return predict_impl(h, rows, n, nullptr, d_out, ld_out);
+}
+
+int di_device_sync(di_handle* h) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    return sync_check(e);
+}
+
+int di_timer_start(di_handle* h) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    DI_CUDA(cudaEventRecord(e.ev_t0, e.stream));
+    return DI_OK;
+}
+
+int di_timer_stop(di_handle* h, float* ms_out) {
+    if (!h || !ms_out) return DI_ERR_ARG;
+    Engine& e = h->e;
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    DI_CUDA(cudaEventRecord(e.ev_t1, e.stream));
+    DI_CUDA(cudaEventSynchronize(e.ev_t1));
+    DI_CUDA(cudaEventElapsedTime(ms_out, e.ev_t0, e.ev_t1));
+    return DI_OK;
+}
+
+int64_t di_launch_count(const di_handle* h) { return h ? h->e.launches : 0; }
+float di_last_device_ms(const di_handle* h) { return h ? h->e.last_ms : -1.f; }
+
+int di_set_profiling(di_handle* h, int32_t on) {
+    if (!h) return DI_ERR_ARG;
+    resolve_timers(h->e);
+    h->e.profiling = on != 0;
+    h->e.kernel_ms.clear();
+    return DI_OK;
+}
+
+float di_kernel_ms(const di_handle* h, const char* which) {
+    if (!h || !which) return -1.f;
+    auto it = h->e.kernel_ms.find(which);
+    if (it == h->e.kernel_ms.end() || it->second.second == 0) return -1.f;
+    return (float)(it->second.first / (double)it->second.second);
+}
+
+int64_t di_kernel_launches(const di_handle* h, const char* which) {
+    if (!h || !which) return 0;
+    auto it = h->e.kernel_ms.find(which);
+    return it == h->e.kernel_ms.end() ? 0 : it->second.second;
+}
+
+int di_debug_read(di_handle* h, const char* which, float* out, int64_t capacity_floats, int64_t* ld) {
+    if (!h || !which || !out || !ld) return DI_ERR_ARG;
+    Engine& e = h->e;
+    const float* src; int64_t pitch;
+    if (!strcmp(which, "h")) { src = e.Hact; pitch = (int64_t)e.S * e.Hp; }
+    else if (!strcmp(which, "dz2")) { src = e.DZ2; pitch = (int64_t)e.S * e.Op; }
+    else if (!strcmp(which, "dz1")) { src = e.DZ1; pitch = (int64_t)e.S * e.Hp; }
+    else return fail(e, DI_ERR_ARG, "di_debug_read: unknown buffer");
+    if (capacity_floats < pitch * e.B) return fail(e, DI_ERR_ARG, "di_debug_read: buffer too small");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    DI_CUDA(cudaMemcpyAsync(out, src, (size_t)pitch * e.B * sizeof(float), cudaMemcpyDeviceToHost, e.stream));
+    *ld = pitch;
+    return sync_check(e);
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// Engine state and kernel-launch interface shared by di_api.cu, kernels_simt.cu and kernels_tc.cu.
+//
+// Data layout in HBM (all fp32, row-major, every pitch a multiple of 32 floats):
+//   norm   [N][G]            log1p(counts), uploaded once (reference multinet.py:217)
+//   X*     [rows][PT]        packed predictor values: sub-network s owns columns coff_s .. coff_s+Pp_s
+//   Y*     [rows][S*Op]      packed target values:    sub-network s owns columns s*Op .. s*Op+O
+//   W1     [PT][Hp]          sub-network s owns rows  coff_s .. coff_s+Pp_s   (Keras layout W[in][out])
+//   W2     [S*Hp][Op]        sub-network s owns rows  s*Hp .. s*Hp+Hp
+//   b1     [S][Hp],  b2 [S][Op];  Adam moments m*, v* mirror the weights
+//   Hact   [rows][S*Hp]      hidden activations after relu (+dropout when training)
+//   DZ2    [B][S*Op], DZ1 [B][S*Hp]   gradients w.r.t. the pre-activations
+// Padding columns/rows hold zeros and stay zero under Adam (g = 0 -> m = v = 0 -> update 0).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/deepimpute_b200.h"
+#include "common.cuh"
+
+namespace di {
+
+struct StepArgs {
+    const float* X;        // [rows][ldx] packed predictors of the batch
+    const float* Y;        // [rows][ldy] packed targets of the batch
+    int64_t ldx, ldy;
+    int64_t row0;          // first row of the batch inside X / Y
+    int32_t n_valid;       // rows of the batch that are real cells (<= B); the rest are zero padding
+    uint32_t step;         // global optimiser step (dropout counter)
+    AdamParams adam;
+};
+
+struct Engine {
+    di_config cfg{};
+    int S = 0, H = 0, O = 0, B = 0, Hp = 0, Op = 0;
+    std::vector<int> P, Pp, gid;
+    std::vector<int64_t> coff;
+    int64_t PT = 0;                 // sum of padded predictor counts
+    int maxPp = 0;
+    SubnetDesc* d_desc = nullptr;   // [S]
+
+    int64_t N = 0, G = 0;
+    float* d_norm = nullptr;
+    int32_t* d_pred_cols = nullptr; // [PT]   gene column of every packed X column, -1 = padding
+    int32_t* d_targ_cols = nullptr; // [S*Op] gene column of every packed Y column, -1 = padding
+    bool have_partition = false;
+
+    float *W1 = nullptr, *mW1 = nullptr, *vW1 = nullptr;
+    float *b1 = nullptr, *mb1 = nullptr, *vb1 = nullptr;
+    float *W2 = nullptr, *mW2 = nullptr, *vW2 = nullptr;
+    float *b2 = nullptr, *mb2 = nullptr, *vb2 = nullptr;
+    int64_t adam_t = 0;
+
+    int32_t *d_train_rows = nullptr, *d_test_rows = nullptr, *d_perm = nullptr;
+    int64_t n_train = 0, n_test = 0, n_train_pad = 0, n_test_pad = 0;
+    float *Xtr = nullptr, *Ytr = nullptr, *Xte = nullptr, *Yte = nullptr;
+
+    float *Xstep = nullptr, *Ystep = nullptr;     // [B][PT], [B][S*Op]   explicit-batch step
+    int32_t* d_step_rows = nullptr;               // [B]
+    float *Hact = nullptr, *DZ2 = nullptr, *DZ1 = nullptr;
+
+    int64_t chunk_rows = 0;                       // inference chunk (multiple of 128)
+    float *Xchunk = nullptr, *Hchunk = nullptr, *Ochunk = nullptr, *OchunkB = nullptr;
+    float* Ochunk2[2] = {nullptr, nullptr};       // {Ochunk, OchunkB}: double buffer of the direct D2H path
+    cudaEvent_t ev_fwd[2] = {nullptr, nullptr};
+    int32_t* d_chunk_rows = nullptr;
+    float* h_pinned[2] = {nullptr, nullptr};      // D2H staging for di_predict
+    cudaEvent_t ev_pinned[2] = {nullptr, nullptr};
+
+    double* d_loss = nullptr;                     // [2]: 0 = training raw sum, 1 = validation raw sum
+
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    float last_ms = 0.f;
+    int64_t launches = 0;
+    bool profiling = false;
+    std::map<std::string, std::pair<double, int64_t>> kernel_ms;   // name -> (total ms, count)
+    struct PendingTimer { const char* name; cudaEvent_t a, b; };
+    std::vector<PendingTimer> pending_timers;                      // recorded, not yet read back
+    std::vector<cudaEvent_t> event_pool;
+    std::string err;
+
+    void* tc = nullptr;                           // tensor-core path state (tensor maps), kernels_tc.cu
+};
+
+// ---- staging ------------------------------------------------------------------------------------------------
+// out[i][j] = norm[row(i)][cols[j]] for i < n_valid and cols[j] >= 0, else 0;  row(i) = rows[perm ? perm[i] : i]
+// (rows == nullptr: row(i) = first_row + i)
+void launch_gather(Engine& e, const int32_t* rows, const int32_t* perm, int64_t first_row, int64_t n_out,
+                   int64_t n_valid, const int32_t* cols, int64_t width, float* out);
+
+// ---- fp32 CUDA-core path (kernels_simt.cu) -------------------------------------------------------------------
+void simt_train_step(Engine& e, const StepArgs& a);
+// forward for `rows` rows of X (multiple of 64): Hbuf [rows][S*Hp] scratch; if Y != nullptr accumulates the raw
+// validation sum into d_loss[1]; if out != nullptr writes yhat to out[rows][ld_out] (column s*O + o).
+void simt_forward(Engine& e, const float* X, int64_t ldx, int64_t rows, int64_t n_valid, float* Hbuf,
+                  const float* Y, int64_t ldy, float* out, int64_t ld_out);
+
+// ---- tcgen05 / TMA path (kernels_tc.cu) ----------------------------------------------------------------------
+bool tc_available();                // false while the tensor-core kernels are not part of the build
+bool tc_init(Engine& e);            // builds tensor maps; false + e.err on failure
+void tc_destroy(Engine& e);
+bool tc_rebind(Engine& e);          // after (re)allocation of X/Y buffers
+void tc_train_step(Engine& e, const StepArgs& a, int which_x);   // which_x: 0 = Xtr/Ytr, 1 = Xstep/Ystep
+void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_valid, bool with_loss,
+                float* out, int64_t ld_out);                     // which_x: 2 = Xte/Yte, 3 = Xchunk
+
+// bias gradients + Adam for b1 and b2 (shared by both paths): db2 = sum_b DZ2, db1 = sum_b DZ1
+void launch_bias_adam(Engine& e, const AdamParams& adam);
+
+void count_launch(Engine& e, const char* name);
+void resolve_timers(Engine& e);   // read back all recorded kernel timings (call after a stream sync)
+struct KernelTimer {   // CUDA-event timing of one launch on e.stream when profiling is on (deferred read-back)
+    Engine& e; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+    KernelTimer(Engine& e_, const char* n);
+    ~KernelTimer();
+};
+
+}  // namespace di

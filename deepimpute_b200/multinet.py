@@ -1,0 +1,414 @@
+"""Host orchestration layer: the reference's ``MultiNet`` with the Keras model swapped for the B200 engine.
+
+Mirrors ``/root/reference/deepimpute/multinet.py`` (signatures ``:67-79``, ``:169-178``, ``:266-269``):
+gene filtering, output-gene partitioning into ``sub_outputdim``-wide sub-networks, predictor selection by
+correlation, the 5 % held-out split and the pandas post-processing all stay in Python and consume the
+legacy ``np.random`` stream in exactly the reference's order (``:183``, ``:326``, ``:340``, ``:219``, ``:228``)
+so that ``targets`` / ``predictors`` / the split are identical for the same seed.  Everything the reference
+hands to Keras (``:226-253``, ``:276-280``) goes to :class:`deepimpute_b200.engine.Engine` instead, which runs
+hand-written sm_100a kernels through the C-ABI in ``include/deepimpute_b200.h``.
+
+Differences kept deliberately small and listed in DESIGN.md: bad input raises ``ValueError`` instead of
+``exit(1)`` (``:46-58``); the duplicate-column mean of ``:284`` is written without ``groupby(axis=1)``
+(removed in pandas 3); ``predict`` uses the weights resident in the engine (and falls back to the saved
+``.npz`` when called on a fresh object) instead of re-loading Keras JSON/HDF5 (``:117-124``).
+"""
+import os
+import tempfile
+import warnings
+
+import numpy as np
+import pandas as pd
+from scipy.stats import pearsonr
+
+from . import partition
+
+
+def _labels(index):
+    """Index labels as a plain object ndarray (pandas 3 string indexes are Arrow-backed and lack ndarray indexing)."""
+    return np.asarray(index, dtype=object)
+
+
+def get_distance_matrix(raw, n_pred=None):
+    """|Pearson r| between candidate predictor genes on RAW counts, as a labelled frame (``multinet.py:20-34``)."""
+    cand = partition.candidate_predictors(raw, n_pred)
+    labels = raw.columns[cand]
+    return pd.DataFrame(partition.abs_correlation(raw.values, cand), index=labels, columns=labels)
+
+
+def wMSE(y_true, y_pred, binary=False):
+    """Weighted MSE of the reference (``multinet.py:36-41``), numpy form: mean over all axes of w*(y-yhat)^2."""
+    y_true = np.asarray(y_true)
+    y_pred = np.asarray(y_pred)
+    weights = (y_true > 0).astype(np.float32) if binary else y_true
+    return np.mean(weights * np.square(y_true - y_pred))
+
+
+def inspect_data(data):
+    """Input sanity checks of ``multinet.py:43-63``; raises ``ValueError`` where the reference calls ``exit(1)``."""
+    if sum(data.index.duplicated()):
+        raise ValueError("ERROR: duplicated cell labels. Please provide unique cell labels.")
+
+    if sum(data.columns.duplicated()):
+        raise ValueError("ERROR: duplicated gene labels. Please provide unique gene labels.")
+
+    max_value = np.max(data.values)
+    if max_value < 10:
+        raise ValueError("ERROR: max value = {}. Is your data log-transformed? Please provide raw counts"
+                         .format(max_value))
+
+    print("Input dataset is {} cells (rows) and {} genes (columns)".format(*data.shape))
+    print("First 3 rows and columns:")
+    print(data.iloc[:3, :3])
+
+
+class MultiNet:
+    """Drop-in for ``deepimpute.multinet.MultiNet`` (reference ``multinet.py:65-375``).
+
+    Extra keyword-only arguments (not in the reference): ``math_mode`` ("tf32" tensor-core kernels, default, or
+    "fp32" CUDA-core kernels), ``device`` (CUDA ordinal) and ``shard`` (a ``parallel.ShardContext``: this process
+    trains only its share of the sub-networks and the per-epoch losses / predicted blocks are exchanged with the
+    other ranks; see ``deepimpute_b200.parallel``).
+    """
+
+    def __init__(self,
+                 learning_rate=1e-4,
+                 batch_size=64,
+                 max_epochs=500,
+                 patience=5,
+                 ncores=-1,
+                 loss="wMSE",
+                 output_prefix=None,
+                 sub_outputdim=512,
+                 verbose=1,
+                 seed=1234,
+                 architecture=None,
+                 *,
+                 math_mode=None,
+                 device=None,
+                 shard=None,
+                 ):
+        self.NN_parameters = {"learning_rate": learning_rate,
+                              "batch_size": batch_size,
+                              "loss": loss,
+                              "architecture": architecture,
+                              "max_epochs": max_epochs,
+                              "patience": patience}
+        self.sub_outputdim = sub_outputdim
+        # reference default is one mkdtemp() shared by every instance (multinet.py:74); one per instance here
+        self.outputdir = output_prefix if output_prefix is not None else tempfile.mkdtemp()
+        self.verbose = verbose
+        self.seed = seed
+        self.setCores(ncores)
+        self.math_mode = math_mode
+        self.shard = shard
+        self.device = device if device is not None else (shard.device if shard is not None else None)
+        self.engine = None
+        self.history = None
+        self._owned = None            # sub-networks of every rank (parallel.assign_subnets); None = unsharded
+
+    def setCores(self, ncores):
+        # kept for API compatibility (multinet.py:92-97); the GPU engine ignores it
+        if ncores > 0:
+            self.ncores = ncores
+        else:
+            self.ncores = os.cpu_count()
+            print("Using all the cores ({})".format(self.ncores))
+
+    def loadDefaultArchitecture(self):
+        self.NN_parameters['architecture'] = [
+            {"type": "dense", "neurons": self.sub_outputdim // 2, "activation": "relu"},
+            {"type": "dropout", "rate": 0.2},
+        ]
+
+    # ---- engine seam (reference: build/save/load, multinet.py:105-167) -------------------------------------
+
+    def _parse_architecture(self):
+        """Reduce the architecture mini-DSL (``multinet.py:135-143``) to (hidden, dropout_rate)."""
+        if self.NN_parameters['architecture'] is None:
+            self.loadDefaultArchitecture()
+        arch = self.NN_parameters['architecture']
+        dense = [l for l in arch if l['type'].lower() == 'dense']
+        drop = [l for l in arch if l['type'].lower() == 'dropout']
+        other = [l for l in arch if l['type'].lower() not in ('dense', 'dropout')]
+        if other:
+            print("Unknown layer type.")
+        if len(dense) != 1 or len(drop) > 1:
+            raise NotImplementedError(
+                "the B200 engine implements the hot-path topology Dense(relu) -> Dropout -> Dense(softplus); "
+                "got {} dense / {} dropout layers".format(len(dense), len(drop)))
+        if dense[0].get('activation', 'relu') != 'relu':
+            raise NotImplementedError("hidden activation must be 'relu'")
+        if drop and arch.index(drop[0]) < arch.index(dense[0]):
+            raise NotImplementedError("dropout must follow the hidden dense layer")
+        rate = float(drop[0]['rate']) if drop else 0.0
+        return int(dense[0]['neurons']), rate
+
+    def _make_engine(self, inputdims, **kwargs):
+        """The one place the CUDA engine is constructed (tests substitute a stand-in here)."""
+        from .engine import Engine
+        return Engine(inputdims, **kwargs)
+
+    def _my_subnets(self, n_subnets):
+        if self._owned is None:
+            return list(range(n_subnets))
+        return self._owned[self.shard.rank]
+
+    def build(self, inputdims):
+        """Create the engine for sub-networks with ``inputdims`` predictors each (reference ``:126-167``).
+
+        Sharded: ``inputdims`` still lists all S sub-networks; this rank's engine holds only the ones
+        ``parallel.assign_subnets`` gives it."""
+        hidden, rate = self._parse_architecture()
+        print(self.NN_parameters['architecture'])
+        loss = self.NN_parameters['loss']
+        if callable(loss):
+            loss = getattr(loss, "__name__", "custom")
+        if loss != "wMSE":
+            raise NotImplementedError("Unknown loss: {}. The B200 engine fuses wMSE (multinet.py:36-41) only."
+                                      .format(loss))
+        if self.shard is not None and self.shard.distributed:
+            from .parallel import assign_subnets
+            self._owned = assign_subnets(inputdims, self.shard.world_size, hidden, self.sub_outputdim)
+        else:
+            self._owned = None
+        mine = self._my_subnets(len(inputdims))
+        if not mine:
+            raise ValueError("rank {} owns no sub-network: use at most {} ranks".format(self.shard.rank,
+                                                                                       len(inputdims)))
+        return self._make_engine([inputdims[s] for s in mine],
+                                 hidden=hidden,
+                                 sub_outputdim=self.sub_outputdim,
+                                 learning_rate=self.NN_parameters['learning_rate'],
+                                 batch_size=self.NN_parameters['batch_size'],
+                                 dropout_rate=rate,
+                                 seed=self.seed if self.seed is not None else 0,
+                                 math_mode=self.math_mode,
+                                 device=self.device,
+                                 subnet_ids=mine)
+
+    def _model_path(self):
+        if self.shard is None or not self.shard.distributed:
+            return "{}/model.npz".format(self.outputdir)
+        return "{}/model.rank{}of{}.npz".format(self.outputdir, self.shard.rank, self.shard.world_size)
+
+    def _predict_matrix(self, model, rows=None):
+        """[n, S*O] float32 = np.hstack(model.predict(...)) over ALL sub-networks (multinet.py:253, :278-280).
+
+        Sharded: every rank computes its own column block and the blocks are all-gathered (NCCL over NVLink when
+        the engine runs on GPUs)."""
+        if self._owned is None:
+            return model.predict(rows=rows)
+        block = model.predict_block(rows=rows)           # torch CUDA tensor (GPU engine) or numpy array
+        return self.shard.gather_blocks(block, self._owned, self.sub_outputdim)
+
+    def save(self, model):
+        os.makedirs(self.outputdir, exist_ok=True)
+        model.save(self._model_path(),
+                   targets=self.targets, predictors=[np.asarray(p) for p in self.predictors])
+        print("Saved model to disk in {}".format(self.outputdir))
+
+    def load(self):
+        from .engine import Engine
+        model, extra = Engine.load(self._model_path(), math_mode=self.math_mode, device=self.device)
+        if not hasattr(self, "targets"):
+            self.targets = extra["targets"]
+            self.predictors = [pd.Index(p) for p in extra["predictors"]]
+        return model
+
+    # ---- fit (reference multinet.py:169-264) -------------------------------------------------------------
+
+    def fit(self,
+            raw,
+            cell_subset=1,
+            NN_lim=None,
+            genes_to_impute=None,
+            n_pred=None,
+            ntop=5,
+            minVMR=0.5,
+            mode='random',
+            ):
+        """Select genes, partition them into sub-networks, train all of them on the GPU, record test metrics."""
+        inspect_data(raw)
+
+        if self.seed is not None:
+            np.random.seed(self.seed)
+
+        if cell_subset != 1:
+            raw = raw.sample(frac=cell_subset) if cell_subset < 1 else raw.sample(int(cell_subset))
+
+        cols = raw.columns
+        self._ranked, self._metric = partition.rank_genes(raw)
+        if genes_to_impute is None:
+            genes = partition.choose_genes(self._ranked, self._metric, self.sub_outputdim, minVMR, NN_lim)
+            print("{} genes selected for imputation".format(len(genes)))
+        else:
+            user = cols.get_indexer(genes_to_impute)
+            if len(user) % self.sub_outputdim != 0:
+                print("The number of input genes is not a multiple of {}. Filling with other genes."
+                      .format(len(user)))
+            genes = partition.pad_user_genes(user, self._ranked, self.sub_outputdim)
+
+        raw_values = raw.values
+        cand = partition.candidate_predictors(raw, n_pred)
+        corr = partition.abs_correlation(raw_values, cand)
+        self._set_partition(cols, raw_values, genes, cand, corr, ntop, mode)
+
+        print("Normalization")
+        norm_values = np.ascontiguousarray(np.log1p(raw_values), dtype=np.float32)
+
+        np.random.seed(self.seed)
+        train_rows, test_rows = partition.split_cells(raw.shape[0], labels=_labels(raw.index))
+        self.train_cells, self.test_cells = _labels(raw.index)[train_rows], _labels(raw.index)[test_rows]
+
+        print("Building network")
+        model = self.build([len(p) for p in self.predictors])
+
+        # The reference materialises 4*S pandas gathers here (multinet.py:231-235); the engine takes the
+        # normalised matrix once plus integer index tables and gathers on the device.
+        pred_idx = [cols.get_indexer(p).astype(np.int32) for p in self.predictors]
+        targ_idx = cols.get_indexer(self.targets.reshape(-1)).reshape(self.targets.shape).astype(np.int32)
+        mine = self._my_subnets(len(pred_idx))
+
+        print("Fitting with {} cells".format(raw.shape[0]))
+        model.set_data(norm_values, [pred_idx[s] for s in mine], targ_idx[mine])
+        # Keras sums the per-branch losses and EarlyStopping watches the sum (multinet.py:242-243): when the
+        # branches live on several GPUs the two scalars are summed over ranks before the stop decision
+        exchange = None
+        if self._owned is not None:
+            exchange = lambda epoch, loss, val: self.shard.sum_scalars(loss, val)   # noqa: E731
+        result = model.fit(train_rows, test_rows,
+                           epochs=self.NN_parameters["max_epochs"],
+                           patience=self.NN_parameters["patience"],
+                           verbose=self.verbose if (self.shard is None or self.shard.rank == 0) else 0,
+                           on_epoch_end=exchange)
+        self.history = result.history
+        self.trained_epochs = len(result.history['loss'])
+        print("Stopped fitting after {} epochs".format(self.trained_epochs))
+
+        self.engine = model
+        self.save(model)
+
+        # held-out metrics on originally non-zero entries (multinet.py:251-262)
+        y_true = norm_values[np.ix_(test_rows, targ_idx.reshape(-1))].reshape(-1)
+        y_hat = self._predict_matrix(model, test_rows).reshape(-1)
+        seen = y_true > 0
+        y_true, y_hat = y_true[seen], y_hat[seen]
+        self.test_metrics = {
+            'correlation': pearsonr(y_true, y_hat)[0],
+            'MSE': np.sum((y_true - y_hat) ** 2) / len(y_true)
+        }
+        return self
+
+    def _set_partition(self, cols, raw_values, genes, cand, corr, ntop, mode):
+        """targets / predictors as labels, from positional partitioning (multinet.py:213-214)."""
+        targ_pos = partition.assign_targets(genes, self.sub_outputdim, mode)
+        where = np.full(len(cols), -1, dtype=np.int64)
+        where[cand] = np.arange(len(cand))
+
+        def corr_rows(_, t):
+            if (where[t] >= 0).all():
+                return corr[where[t]]
+            # only reachable with n_pred (the reference raises KeyError here, multinet.py:356-358):
+            # rows = all targets, columns = the n_pred candidates
+            return partition.abs_correlation(raw_values, t, cand)
+
+        pred_pos = partition.choose_predictors(targ_pos, cand, _labels(cols)[cand], corr_rows, ntop)
+        self.targets = _labels(cols)[targ_pos]
+        self.predictors = [cols[p] for p in pred_pos]
+
+    # ---- predict (reference multinet.py:266-310) ---------------------------------------------------------
+
+    def predict(self,
+                raw,
+                imputed_only=False,
+                policy="restore"):
+
+        norm_raw = np.log1p(raw)
+        norm_values = norm_raw.values
+
+        model = self.engine if self.engine is not None else self.load()
+
+        cols = raw.columns
+        pred_idx = [cols.get_indexer(p).astype(np.int32) for p in self.predictors]
+        targets_flat = self.targets.flatten()
+        targ_pos = cols.get_indexer(targets_flat)
+        targ_idx = targ_pos.reshape(self.targets.shape).astype(np.int32)
+        if self.shard is not None and self.shard.distributed and self._owned is None:
+            from .parallel import assign_subnets
+            self._owned = assign_subnets([len(p) for p in pred_idx], self.shard.world_size, model.H, model.O)
+        mine = self._my_subnets(len(pred_idx))
+        model.set_data(np.ascontiguousarray(norm_values, dtype=np.float32), [pred_idx[s] for s in mine],
+                       targ_idx[mine])
+
+        predicted = self._predict_matrix(model)           # [N, S*O] float32, columns = targets.flatten()
+
+        # mean over duplicated target columns (multinet.py:284), groups in sorted label order
+        uniq_labels, inverse, counts = np.unique(targets_flat, return_inverse=True, return_counts=True)
+        uniq_pos = cols.get_indexer(uniq_labels)
+        if len(uniq_labels) == len(targets_flat):
+            pred_u = predicted[:, np.argsort(inverse, kind="stable")]
+        else:
+            acc = np.zeros((predicted.shape[0], len(uniq_labels)), dtype=np.float64)
+            order = np.argsort(inverse, kind="stable")
+            starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+            acc[:] = np.add.reduceat(predicted[:, order].astype(np.float64), starts, axis=1)
+            pred_u = (acc / counts).astype(np.float32)
+
+        imputed = np.array(norm_values, dtype=np.float64, copy=True)
+        imputed[:, uniq_pos] = pred_u
+
+        # To prevent overflow
+        imputed[(imputed > 2 * norm_values.max()) | (np.isnan(imputed))] = 0
+        # Convert back to counts
+        imputed = np.expm1(imputed)
+
+        if policy == "restore":
+            print("Filling zeros")
+            mask = (raw.values > 0)
+            imputed[mask] = raw.values[mask]
+        elif policy == "max":
+            print("Imputing data with 'max' policy")
+            mask = (raw.values > imputed)
+            imputed[mask] = raw.values[mask]
+
+        imputed = pd.DataFrame(imputed, index=raw.index, columns=raw.columns)
+
+        if imputed_only:
+            return imputed.loc[:, uniq_labels]
+        else:
+            return imputed
+
+    # ---- reference-named entry points for the partitioning steps (multinet.py:312-365) ------------------
+
+    def filter_genes(self, gene_metric, threshold, NN_lim=None):
+        """``gene_metric``: Series sorted descending, as in the reference; returns gene labels."""
+        pos = partition.choose_genes(np.arange(len(gene_metric)), gene_metric.values,
+                                     self.sub_outputdim, threshold, NN_lim)
+        print("{} genes selected for imputation".format(len(pos)))
+        return _labels(gene_metric.index)[pos]
+
+    def setTargets(self, data, mode='random'):
+        pos = partition.assign_targets(np.arange(data.shape[1]), self.sub_outputdim, mode)
+        self.targets = _labels(data.columns)[pos]
+
+    def setPredictors(self, covariance_matrix, ntop=5):
+        labels = covariance_matrix.columns
+        values = covariance_matrix.values
+        row_of = pd.Series(np.arange(len(covariance_matrix.index)), index=covariance_matrix.index)
+        targ_pos = [labels.get_indexer(t) for t in self.targets]          # -1 = target is no candidate
+
+        def corr_rows(i, _):
+            return values[row_of.loc[self.targets[i]].values]
+
+        pred = partition.choose_predictors(targ_pos, np.arange(len(labels)), _labels(labels), corr_rows, ntop)
+        self.predictors = [labels[p] for p in pred]
+
+    def score(self, data, policy=None):
+        warnings.warn(
+            "This method is deprecated. Please use model.test_metrics to measure model accuracy instead",
+            DeprecationWarning)
+        Y_hat = self.predict(data, policy=policy)
+        Y = data.loc[Y_hat.index, Y_hat.columns]
+
+        return pearsonr(Y_hat.values.reshape(-1), Y.values.reshape(-1))

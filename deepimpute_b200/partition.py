@@ -1,0 +1,142 @@
+"""Gene selection, output-gene partitioning and predictor selection in positional (integer) index space.
+
+These are the host-side steps of the reference that decide *what* the engine trains: how many sub-networks
+there are, which 512 genes each one outputs and which genes feed it.  They must give the same answer as the
+reference for the same ``np.random`` seed, so every draw from the legacy global stream happens here in the
+reference's order and with calls that consume the stream identically:
+
+=====================  ===============================  =============================================
+step                   reference                        draw
+=====================  ===============================  =============================================
+filler genes           ``multinet.py:326`` / ``:207``   ``choice(n, rest)``  (with replacement)
+target partition       ``multinet.py:340-342``          ``choice(n, [S, O], replace=False)``
+held-out cells         ``multinet.py:228``              ``choice(N, int(0.05*N), replace=False)``
+=====================  ===============================  =============================================
+
+``np.random.choice(labels, ...)`` draws integer positions and then indexes ``labels``; drawing positions
+directly is the same stream, so everything below works on positions and the caller maps back to labels.
+"""
+import warnings
+
+import numpy as np
+import pandas as pd
+
+
+def rank_genes(raw):
+    """Positions of genes with var/(1+mean) > 0, best first (reference ``multinet.py:191-192``).
+
+    pandas reductions and ``sort_values`` are used on purpose: their summation order and tie-breaking are what
+    the reference sees.
+    """
+    metric = raw.var() / (1 + raw.mean())
+    metric = pd.Series(metric.values, index=np.arange(raw.shape[1])).sort_values(ascending=False)
+    metric = metric[metric > 0]
+    return metric.index.values.astype(np.int64), metric.values
+
+
+def choose_genes(ranked, metric_values, sub_outputdim, threshold, limit=None):
+    """Genes to impute, padded with random filler genes to a multiple of ``sub_outputdim``.
+
+    Follows ``filter_genes`` (``multinet.py:312-331``), including its quirk: the pad length is
+    ``O - (len % O)``, which is a whole extra sub-network of random genes when ``len % O == 0``.
+    """
+    if not str(limit).isdigit():
+        limit = int((metric_values > threshold).sum())
+    n_nets = int(np.ceil(int(limit) / sub_outputdim))
+    chosen = ranked[:n_nets * sub_outputdim]
+    pad = sub_outputdim - (len(chosen) % sub_outputdim)
+    if pad > 0:
+        chosen = np.concatenate([chosen, ranked[np.random.choice(len(ranked), pad)]])
+    return chosen
+
+
+def pad_user_genes(user_genes, ranked, sub_outputdim):
+    """User-supplied gene list padded up to one sub-network (``multinet.py:196-209``; only meaningful < O)."""
+    n = len(user_genes)
+    if n % sub_outputdim == 0:
+        return np.asarray(user_genes)
+    filler = ranked[:max(sub_outputdim - n, 0)]
+    short = sub_outputdim - n - len(filler)
+    if short > 0:
+        filler = np.concatenate([filler, ranked[np.random.choice(len(ranked), short, replace=True)]])
+    return np.concatenate([np.asarray(user_genes), filler])
+
+
+def assign_targets(genes, sub_outputdim, mode="random"):
+    """[S, O] target genes per sub-network (``setTargets``, ``multinet.py:333-342``)."""
+    n_nets = int(len(genes) / sub_outputdim)
+    if mode == "progressive":
+        return np.asarray(genes)[:n_nets * sub_outputdim].reshape(n_nets, sub_outputdim)
+    pick = np.random.choice(len(genes), [n_nets, sub_outputdim], replace=False)
+    return np.asarray(genes)[pick]
+
+
+def candidate_predictors(raw, n_pred=None):
+    """Positions of candidate predictor genes: std/mean > 0, or the top ``n_pred`` of it (``multinet.py:22-29``)."""
+    cv = raw.std() / raw.mean()
+    cv[np.isinf(cv)] = 0
+    cv = pd.Series(cv.values, index=np.arange(raw.shape[1]))
+    if n_pred is None:
+        return np.flatnonzero((cv > 0).values)
+    print("Using {} predictors".format(n_pred))
+    return cv.sort_values(ascending=False).index.values[:n_pred].astype(np.int64)
+
+
+def abs_correlation(raw_values, rows, cols=None):
+    """|corrcoef| of gene columns ``rows`` x ``cols`` on raw counts, NaN -> 0 (``multinet.py:31-33``).
+
+    With ``cols is None`` this is exactly ``np.abs(np.corrcoef(raw.T.loc[rows]))``.
+    """
+    if cols is None:
+        c = np.abs(np.corrcoef(raw_values[:, rows].T))
+        return np.nan_to_num(c, nan=0.0, posinf=np.inf, neginf=-np.inf)
+    x = np.asarray(raw_values, dtype=np.float64)
+    a = x[:, rows] - x[:, rows].mean(0)
+    b = x[:, cols] - x[:, cols].mean(0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        c = (a.T @ b) / np.sqrt(np.outer((a * a).sum(0), (b * b).sum(0)))
+    return np.nan_to_num(np.abs(np.clip(c, -1, 1)), nan=0.0)
+
+
+def choose_predictors(targets, cand, cand_labels, corr_rows, ntop=5):
+    """Predictor genes of every sub-network (``setPredictors``, ``multinet.py:344-365``).
+
+    ``targets``      [S, O] gene positions.
+    ``cand``         candidate gene positions, in correlation-matrix column order.
+    ``cand_labels``  their labels: the reference takes ``np.setdiff1d`` on *labels*, so the surviving
+                     candidates are visited in label-sorted order and ties in the top-``ntop`` break that way.
+    ``corr_rows``    callable ``(subnet, target_positions) -> [len, len(cand)]`` |r| rows.
+
+    Per target: the ``ntop`` most correlated candidates outside the sub-network's own targets; per sub-network:
+    their union in first-appearance order.
+    """
+    cand = np.asarray(cand)
+    label_order = np.argsort(np.asarray(cand_labels), kind="stable")      # np.setdiff1d returns sorted labels
+    out = []
+    for i, t in enumerate(targets):
+        keep = label_order[~np.isin(cand[label_order], t)]
+        if keep.size == 0:
+            warnings.warn('Warning: number of target genes lower than output dim. Consider lowering down the '
+                          'sub_outputdim parameter', UserWarning)
+            keep = np.arange(len(cand))
+        sub = corr_rows(i, t)[:, keep]
+        top = np.argsort(-sub, axis=1)[:, :ntop].ravel()
+        picked = pd.unique(cand[keep][top])
+        out.append(picked.astype(np.int64))
+        print("Net {}: {} predictors, {} targets".format(i, len(picked), len(t)))
+    return out
+
+
+def split_cells(n_cells, labels=None):
+    """5 % held-out cells (``multinet.py:228-229``): returns (train_rows, test_rows).
+
+    Test rows keep draw order; train rows are sorted by *label* because the reference builds them with
+    ``np.setdiff1d`` on the index labels.
+    """
+    test = np.random.choice(n_cells, int(0.05 * n_cells), replace=False)
+    mask = np.ones(n_cells, dtype=bool)
+    mask[test] = False
+    train = np.flatnonzero(mask)
+    if labels is not None:
+        train = train[np.argsort(np.asarray(labels)[train], kind="stable")]
+    return train.astype(np.int32), test.astype(np.int32)

@@ -1,0 +1,253 @@
+"""Parity tests proper: the CUDA engine, called through the C-ABI, against the CPU oracle on the same seeded inputs
+(same initial weights, same batches, same Philox dropout masks).
+
+Tolerances (stated per north_star "within a stated fp32 tolerance"):
+  fp32 mode  -- CUDA-core FFMA; differs from the oracle only by summation order.  Forward 1e-5 relative, Adam first
+                moments 1e-5 of their scale, weights after k steps within 1e-5 + steps*2e-7 absolute.
+  tf32 mode  -- tcgen05 kind::tf32 (operands truncated to 10 mantissa bits, fp32 accumulate).  Compared with the
+                fp32 oracle at 3e-3 relative on activations, and with the oracle run in operand-truncation mode
+                (same rounding as the tensor core) at 1e-4.
+"""
+import numpy as np
+import pytest
+
+from deepimpute_b200 import _lib
+from deepimpute_b200.engine import Engine, epoch_permutation
+from oracle.multinet_oracle import OracleNet, stage
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = {"fp32": 2e-5, "tf32": 4e-3}
+MOM_TOL = {"fp32": 2e-5, "tf32": 6e-3}
+
+
+def modes():
+    lib = _lib.load()
+    return [m for m, code in _lib.DI_MATH.items() if lib.di_math_mode_available(code)]
+
+
+def make_problem(n_cells, n_genes, n_pred, O, seed):
+    rng = np.random.default_rng(seed)
+    lam = rng.gamma(0.6, 3.0, size=(1, n_genes)) * rng.gamma(2.0, 0.5, size=(n_cells, 1))
+    norm = np.log1p(rng.poisson(lam)).astype(np.float32)
+    perm = rng.permutation(n_genes)
+    S = len(n_pred)
+    targ_idx = perm[:S * O].reshape(S, O).astype(np.int32)
+    rest = perm[S * O:] if n_genes > S * O + max(n_pred) else perm
+    pred_idx = [rng.choice(rest, p, replace=False).astype(np.int32) for p in n_pred]
+    return norm, pred_idx, targ_idx
+
+
+def pair(n_pred, H, O, B, mode, seed=7, lr=1e-3, rate=0.2, oracle_round=None):
+    eng = Engine(n_pred, hidden=H, sub_outputdim=O, learning_rate=lr, batch_size=B, dropout_rate=rate, seed=seed,
+                 math_mode=mode)
+    ref = OracleNet(n_pred, H, O, learning_rate=lr, batch_size=B, dropout_rate=rate, seed=seed,
+                    operand_round=oracle_round)
+    return eng, ref
+
+
+def rel_err(a, b, floor=1e-3):
+    return float(np.max(np.abs(a - b) / (np.abs(b) + floor)))
+
+
+SHAPES = [
+    # n_pred, H, O, B   (ragged P, H not a multiple of 32 as in reference tests: 150 / 300)
+    ([70, 33, 96], 48, 64, 64),
+    ([303, 296, 284], 150, 512, 64),           # reference tests/multinet_test.py set-up
+    ([1], 8, 8, 4),                            # degenerate: one predictor
+    ([600], 256, 512, 64),                     # default topology, one sub-network
+    ([129, 2, 64, 31, 257], 300, 96, 32),      # O not a multiple of 32, H = 300 (deepImpute_test.py)
+]
+
+
+@pytest.mark.parametrize("mode", modes())
+@pytest.mark.parametrize("n_pred,H,O,B", SHAPES)
+def test_forward_matches_oracle(mode, n_pred, H, O, B):
+    norm, pred_idx, targ_idx = make_problem(200, max(1200, sum(n_pred)), n_pred, O, seed=1)
+    eng, ref = pair(n_pred, H, O, B, mode)
+    eng.set_data(norm, pred_idx, targ_idx)
+    X, _ = stage(norm, pred_idx, targ_idx, np.arange(norm.shape[0]))
+    want = np.hstack(ref.forward(X))
+    got = eng.predict()
+    assert got.shape == want.shape
+    assert rel_err(got, want) < FWD_TOL[mode]
+    rows = np.array([5, 199, 0, 17, 17], dtype=np.int32)            # arbitrary order, duplicates allowed
+    np.testing.assert_allclose(eng.predict(rows=rows), got[rows], rtol=0, atol=0)
+    assert eng.predict(rows=np.zeros(0, np.int32)).shape == (0, len(n_pred) * O)
+    eng.close()
+
+
+@pytest.mark.parametrize("mode", modes())
+@pytest.mark.parametrize("n_pred,H,O,B", SHAPES)
+@pytest.mark.parametrize("nrows", ["full", "partial"])
+def test_single_step_matches_oracle(mode, n_pred, H, O, B, nrows):
+    """Loss, every intermediate (h, dz2, dz1), Adam first/second moments and the updated weights of one step."""
+    norm, pred_idx, targ_idx = make_problem(150, max(1200, sum(n_pred)), n_pred, O, seed=2)
+    eng, ref = pair(n_pred, H, O, B, mode)
+    eng.set_data(norm, pred_idx, targ_idx)
+    n = B if nrows == "full" else max(1, B - 5)
+    rows = np.random.default_rng(3).choice(150, n, replace=False).astype(np.int32)
+    X, Y = stage(norm, pred_idx, targ_idx, rows)
+    step = 4
+    inter = [ref.gradients(s, X[s], Y[s], step)[2] for s in range(len(n_pred))]
+    grads = [ref.gradients(s, X[s], Y[s], step)[1] for s in range(len(n_pred))]
+    ref.t = step
+    loss_ref = ref.train_step(X, Y, step)
+    loss = eng.train_step(rows, step)
+    assert loss == pytest.approx(loss_ref, rel=FWD_TOL[mode] * 5)
+
+    Hp = -(-H // 32) * 32
+    Op = -(-O // 32) * 32
+    h, dz2, dz1 = eng.debug_read("h"), eng.debug_read("dz2"), eng.debug_read("dz1")
+    for s in range(len(n_pred)):
+        hs = h[:n, s * Hp:s * Hp + H]
+        # dropout masks are bit-identical: the same units are zero
+        assert np.array_equal(hs == 0, inter[s]["h"].numpy() == 0) or mode != "fp32"
+        assert rel_err(hs, inter[s]["h"].numpy()) < FWD_TOL[mode]
+        scale2 = np.abs(inter[s]["dz2"].numpy()).max() + 1e-30
+        assert np.max(np.abs(dz2[:n, s * Op:s * Op + O] - inter[s]["dz2"].numpy())) / scale2 < MOM_TOL[mode]
+        scale1 = np.abs(inter[s]["dz1"].numpy()).max() + 1e-30
+        assert np.max(np.abs(dz1[:n, s * Hp:s * Hp + H] - inter[s]["dz1"].numpy())) / scale1 < MOM_TOL[mode]
+        # padding rows (beyond the partial batch) and padding columns carry nothing
+        assert not dz2[n:, s * Op:(s + 1) * Op].any() and not dz1[n:, s * Hp:(s + 1) * Hp].any()
+        assert not dz2[:, s * Op + O:(s + 1) * Op].any() and not h[:, s * Hp + H:(s + 1) * Hp].any()
+
+    for s in range(len(n_pred)):
+        bufs, t = eng.get_adam_state(s)
+        assert t == step + 1
+        for k in range(4):
+            g = grads[s][k].numpy()
+            m_gpu, v_gpu = bufs[2 * k], bufs[2 * k + 1]
+            scale = np.abs(g).max() + 1e-30
+            assert np.max(np.abs(m_gpu / (1 - np.float32(0.9)) - g)) / scale < MOM_TOL[mode]
+            assert np.max(np.abs(v_gpu / (1 - np.float32(0.999)) - g * g)) / scale ** 2 < 2 * MOM_TOL[mode]
+    if mode == "fp32":
+        for w_gpu, w_ref in zip(eng.get_weights(), ref.get_weights()):
+            for a, b in zip(w_gpu, w_ref):
+                assert np.max(np.abs(a - b)) < 1e-5            # lr = 1e-3: a wrong-sign update would be 2e-3
+    eng.close()
+
+
+@pytest.mark.parametrize("mode", modes())
+def test_epochs_match_oracle(mode):
+    """Three epochs with shuffling, a partial last batch and the validation pass: Keras' `loss`/`val_loss`."""
+    n_pred, H, O, B = [90, 41], 40, 64, 32
+    norm, pred_idx, targ_idx = make_problem(240, 900, n_pred, O, seed=5)
+    eng, ref = pair(n_pred, H, O, B, mode, lr=5e-4)
+    eng.set_data(norm, pred_idx, targ_idx)
+    rng = np.random.default_rng(1)
+    cells = rng.permutation(240)
+    test_rows, train_rows = cells[:13].astype(np.int32), np.sort(cells[13:]).astype(np.int32)   # 227 = 7*32 + 3
+    eng.set_split(train_rows, test_rows)
+    Xtr, Ytr = stage(norm, pred_idx, targ_idx, train_rows)
+    Xte, Yte = stage(norm, pred_idx, targ_idx, test_rows)
+    assert eng.validation_loss() == pytest.approx(ref.loss(Xte, Yte), rel=FWD_TOL[mode] * 5)
+    step = 0
+    tol = 5e-5 if mode == "fp32" else 2e-2
+    for e in range(3):
+        perm = epoch_permutation(7, e, len(train_rows))
+        loss_ref, step = ref.train_epoch(Xtr, Ytr, perm, step)
+        val_ref = ref.loss(Xte, Yte)
+        loss, val = eng.train_epoch(perm)
+        assert loss == pytest.approx(loss_ref, rel=tol)
+        assert val == pytest.approx(val_ref, rel=tol)
+    assert eng.steps_done == step == 24
+    want = np.hstack(ref.forward(stage(norm, pred_idx, targ_idx, np.arange(240))[0]))
+    assert rel_err(eng.predict(), want) < (2e-4 if mode == "fp32" else 3e-2)
+    eng.close()
+
+
+@pytest.mark.parametrize("mode", modes())
+def test_fit_early_stopping_and_keras_adapters(mode):
+    n_pred, H, O, B = [20, 24], 16, 32, 16
+    norm, pred_idx, targ_idx = make_problem(120, 400, n_pred, O, seed=8)
+    eng, ref = pair(n_pred, H, O, B, mode, lr=2e-3)
+    train_rows, test_rows = np.arange(100, dtype=np.int32), np.arange(100, 120, dtype=np.int32)
+    Xtr, Ytr = stage(norm, pred_idx, targ_idx, train_rows)
+    Xte, Yte = stage(norm, pred_idx, targ_idx, test_rows)
+    # Keras-shaped call: lists of arrays, as reference multinet.py:238-244 passes them
+    hist = eng.fit_arrays(Xtr, Ytr, (Xte, Yte), epochs=6, patience=2, verbose=0)
+    want = ref.fit(Xtr, Ytr, Xte, Yte, epochs=6, patience=2)
+    assert len(hist.history["loss"]) == len(want["loss"])
+    np.testing.assert_allclose(hist.history["val_loss"], want["val_loss"], rtol=1e-4 if mode == "fp32" else 3e-2)
+    parts = eng.predict_arrays(Xte)                         # list of S arrays [n, O] like model.predict
+    assert len(parts) == 2 and parts[0].shape == (20, O)
+    assert rel_err(np.hstack(parts), np.hstack(ref.forward(Xte))) < (2e-4 if mode == "fp32" else 3e-2)
+    eng.close()
+
+
+def test_sharded_engines_reproduce_the_unsharded_model():
+    """Global sub-network ids key init and dropout: two handles owning {0,2} and {1} == one handle owning all."""
+    n_pred, H, O, B = [50, 60, 70], 32, 32, 32
+    norm, pred_idx, targ_idx = make_problem(100, 500, n_pred, O, seed=9)
+    rows = np.arange(32, dtype=np.int32)
+    full = Engine(n_pred, hidden=H, sub_outputdim=O, batch_size=B, seed=5, math_mode="fp32")
+    full.set_data(norm, pred_idx, targ_idx)
+    full.train_step(rows, 0)
+    want = full.get_weights()
+    for own in ([0, 2], [1]):
+        part = Engine([n_pred[s] for s in own], hidden=H, sub_outputdim=O, batch_size=B, seed=5, math_mode="fp32",
+                      subnet_ids=own)
+        part.set_data(norm, [pred_idx[s] for s in own], targ_idx[own])
+        part.train_step(rows, 0)
+        for k, s in enumerate(own):
+            for a, b in zip(part.get_weights()[k], want[s]):
+                np.testing.assert_array_equal(a, b)
+        part.close()
+    full.close()
+
+
+def test_predict_device_writes_strided_block():
+    import torch
+    n_pred, H, O = [40, 30], 16, 32
+    norm, pred_idx, targ_idx = make_problem(300, 300, n_pred, O, seed=4)
+    eng = Engine(n_pred, hidden=H, sub_outputdim=O, math_mode="fp32")
+    eng.set_data(norm, pred_idx, targ_idx)
+    want = eng.predict()
+    buf = torch.full((300, 100), -1.0, device="cuda")
+    eng.predict_device(buf[:, 10:].data_ptr(), 100)
+    torch.cuda.synchronize()
+    got = buf.cpu().numpy()
+    np.testing.assert_array_equal(got[:, 10:10 + 2 * O], want)
+    assert (got[:, :10] == -1).all() and (got[:, 10 + 2 * O:] == -1).all()
+    eng.close()
+
+
+def test_errors_are_reported_not_swallowed():
+    eng = Engine([10], hidden=8, sub_outputdim=8, math_mode="fp32")
+    with pytest.raises(RuntimeError, match="set_data"):
+        eng.predict()
+    with pytest.raises(RuntimeError, match="no data"):
+        eng.train_step(np.arange(4))
+    norm = np.ones((20, 30), np.float32)
+    with pytest.raises(ValueError):
+        eng.set_data(norm, [np.arange(9)], np.arange(8).reshape(1, 8))
+    with pytest.raises(ValueError, match="out of range"):
+        eng.set_data(norm, [np.arange(10) + 25], np.arange(8).reshape(1, 8))
+    eng.set_data(norm, [np.arange(10)], np.arange(10, 18).reshape(1, 8))
+    with pytest.raises(RuntimeError, match="1..B"):
+        eng.train_step(np.arange(20) % 20, 0) if eng.B < 20 else eng.train_step(np.zeros(0, np.int32), 0)
+    with pytest.raises(RuntimeError, match="di_set_split"):
+        eng.train_epoch(np.zeros(0, np.int32))
+    with pytest.raises(ValueError, match="math_mode"):
+        Engine([10], math_mode="fp8")
+    eng.close()
+    eng.close()                                            # idempotent
+
+
+def test_save_load_roundtrip(tmp_path):
+    n_pred, H, O = [12, 9], 8, 16
+    norm, pred_idx, targ_idx = make_problem(64, 200, n_pred, O, seed=6)
+    eng = Engine(n_pred, hidden=H, sub_outputdim=O, batch_size=16, math_mode="fp32", seed=3)
+    eng.set_data(norm, pred_idx, targ_idx)
+    eng.train_step(np.arange(16), 0)
+    want = eng.predict()
+    path = str(tmp_path / "model.npz")
+    eng.save(path, targets=np.array([["a", "b"], ["c", "d"]], dtype=object), predictors=[np.array(["x"]), np.array(["y", "z"])])
+    eng.close()
+    again, extra = Engine.load(path, math_mode="fp32")
+    again.set_data(norm, pred_idx, targ_idx)
+    np.testing.assert_array_equal(again.predict(), want)
+    assert extra["targets"].tolist() == [["a", "b"], ["c", "d"]]
+    assert [list(p) for p in extra["predictors"]] == [["x"], ["y", "z"]]
+    again.close()

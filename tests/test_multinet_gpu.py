@@ -1,0 +1,92 @@
+"""End-to-end through the reference-facing API on the GPU: MultiNet.fit / predict and deepImpute() on the reference's
+own example matrix (examples/test.csv, shipped as tests/golden/test_counts.npz), mirroring the reference's smoke
+tests (tests/multinet_test.py:12-33, tests/deepImpute_test.py:8-32) -- plus what they do not check: parity of the
+imputed matrix with the CPU oracle for the same seeds at a fixed epoch count."""
+import numpy as np
+import pytest
+
+from conftest import synthetic_counts
+from deepimpute_b200 import MultiNet, deepImpute
+from deepimpute_b200.engine import epoch_permutation
+from oracle.multinet_oracle import OracleNet, stage
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_multinet_test_flow(test_counts):
+    # reference tests/multinet_test.py:14-31
+    raw = test_counts[test_counts.quantile(.99).sort_values(ascending=False).index[0:1300]]
+    model = MultiNet(architecture=[{"type": "dense", "neurons": 150, "activation": "relu"},
+                                   {"type": "dropout", "rate": 0.2}],
+                     loss="wMSE", sub_outputdim=512, seed=123, ncores=2, max_epochs=30, verbose=0)
+    model.fit(raw)
+    out = model.predict(raw, policy="restore")
+    assert out.shape == raw.shape
+    assert [len(p) for p in model.predictors] == [303, 296, 284]
+    assert np.isfinite(out.values).all() and (out.values >= 0).all()
+    mask = raw.values > 0
+    assert np.array_equal(out.values[mask], raw.values[mask])
+    assert (out.values[~mask] > 0).mean() > 0.5                      # zeros of imputed genes get filled in
+    assert model.test_metrics["correlation"] > 0.7
+    assert 1 <= model.trained_epochs <= 30
+    # a fresh object pointed at the same output_prefix predicts from the saved model (multinet.py:117-124)
+    again = MultiNet(output_prefix=model.outputdir, sub_outputdim=512, ncores=2, verbose=0)
+    out2 = again.predict(raw)
+    np.testing.assert_allclose(out2.values, out.values, rtol=1e-6)
+
+
+def test_fit_predict_matches_oracle_at_fixed_epochs(test_counts):
+    """Config c1 (test.csv, defaults, seed 1234) for 5 epochs: imputed values within 1e-3 relative of the oracle."""
+    raw = test_counts
+    net = MultiNet(seed=1234, ncores=1, max_epochs=5, patience=100, verbose=0, math_mode="fp32")
+    net.fit(raw)
+    assert [len(p) for p in net.predictors] == [639, 592, 592, 594, 555, 631]
+    got = net.predict(raw, policy="restore")
+
+    cols = raw.columns
+    norm = np.log1p(raw.values).astype(np.float32)
+    pred_idx = [cols.get_indexer(p) for p in net.predictors]
+    targ_idx = cols.get_indexer(net.targets.reshape(-1)).reshape(net.targets.shape)
+    train_rows = raw.index.get_indexer(net.train_cells)
+    test_rows = raw.index.get_indexer(net.test_cells)
+    ref = OracleNet([len(p) for p in pred_idx], 256, 512, seed=1234)
+    Xtr, Ytr = stage(norm, pred_idx, targ_idx, train_rows)
+    Xte, Yte = stage(norm, pred_idx, targ_idx, test_rows)
+    step, losses, vals = 0, [], []
+    for e in range(5):
+        loss, step = ref.train_epoch(Xtr, Ytr, epoch_permutation(1234, e, len(train_rows)), step)
+        losses.append(loss)
+        vals.append(ref.loss(Xte, Yte))
+    np.testing.assert_allclose(net.history["loss"], losses, rtol=1e-4)
+    np.testing.assert_allclose(net.history["val_loss"], vals, rtol=1e-4)
+    want = np.hstack(ref.forward(stage(norm, pred_idx, targ_idx, np.arange(len(raw)))[0]))
+    flat = targ_idx.reshape(-1)
+    uniq, first = np.unique(flat, return_index=True)
+    dup = np.setdiff1d(np.arange(len(flat)), first)
+    single = np.setdiff1d(uniq, flat[dup])                 # genes predicted by exactly one output unit
+    where = {g: i for i, g in enumerate(flat)}
+    sel = np.array([where[g] for g in single])
+    zero = raw.values[:, single] == 0
+    imputed_ref = np.expm1(want[:, sel].astype(np.float64))
+    rel = np.abs(got.values[:, single] - imputed_ref) / (np.abs(imputed_ref) + 1e-3)
+    assert rel[zero].max() < 1e-3
+
+
+def test_deepimpute_entry_point(tmp_path, test_counts):
+    # reference tests/deepImpute_test.py:8-32 (limit 1000, hidden 300, lr 1e-4), fewer epochs
+    path = tmp_path / "test.csv"
+    test_counts.to_csv(path)
+    out = deepImpute(inputFile=str(path), output=None, cores=1, cell_axis="rows", limit="1000", minVMR=0.5, subset=1,
+                     learning_rate=1e-4, batch_size=64, max_epochs=3, hidden_neurons=300, dropout_rate=0.2,
+                     output_neurons=512, n_pred=None, policy="restore")
+    assert out.shape == test_counts.shape and np.isfinite(out.values).all()
+
+
+def test_small_inputs_and_user_gene_list():
+    raw = synthetic_counts(90, 70, seed=4)
+    net = MultiNet(ncores=1, sub_outputdim=16, max_epochs=2, verbose=0,
+                   architecture=[{"type": "dense", "neurons": 12, "activation": "relu"}, {"type": "dropout", "rate": 0.5}])
+    net.fit(raw, genes_to_impute=list(raw.columns[:10]), minVMR=0.0)          # padded up to one sub-network
+    assert net.targets.shape == (1, 16)
+    out = net.predict(raw, imputed_only=True)
+    assert out.shape[0] == 90 and set(raw.columns[:10]) <= set(out.columns)
