@@ -179,6 +179,7 @@ int di_create(di_handle** out, const di_config* cfg, const int32_t* n_pred) {
     Engine& e = h->e;
     e.cfg = *cfg;
     e.S = cfg->n_subnets; e.H = cfg->hidden; e.O = cfg->sub_outputdim; e.B = cfg->batch_size;
+    e.Bp = round_up(e.B, 32);          // rows of every per-step buffer; batch i is staged at rows [i*Bp, i*Bp + B)
     e.Hp = round_up(e.H, 32); e.Op = round_up(e.O, 32);
     e.P.assign(n_pred, n_pred + e.S);
     e.Pp.resize(e.S); e.coff.resize(e.S);
@@ -214,12 +215,12 @@ int di_create(di_handle** out, const di_config* cfg, const int32_t* n_pred) {
         }
         if ((rc = dev_alloc(e, &e.d_pred_cols, e.PT))) return rc;
         if ((rc = dev_alloc(e, &e.d_targ_cols, nb2))) return rc;
-        if ((rc = dev_alloc(e, &e.Xstep, (int64_t)e.B * e.PT))) return rc;
-        if ((rc = dev_alloc(e, &e.Ystep, (int64_t)e.B * nb2))) return rc;
-        if ((rc = dev_alloc(e, &e.d_step_rows, e.B))) return rc;
-        if ((rc = dev_alloc(e, &e.Hact, (int64_t)e.B * nb1))) return rc;
-        if ((rc = dev_alloc(e, &e.DZ2, (int64_t)e.B * nb2))) return rc;
-        if ((rc = dev_alloc(e, &e.DZ1, (int64_t)e.B * nb1))) return rc;
+        if ((rc = dev_alloc(e, &e.Xstep, (int64_t)e.Bp * e.PT))) return rc;
+        if ((rc = dev_alloc(e, &e.Ystep, (int64_t)e.Bp * nb2))) return rc;
+        if ((rc = dev_alloc(e, &e.d_step_rows, e.Bp))) return rc;
+        if ((rc = dev_alloc(e, &e.Hact, (int64_t)e.Bp * nb1))) return rc;
+        if ((rc = dev_alloc(e, &e.DZ2, (int64_t)e.Bp * nb2))) return rc;
+        if ((rc = dev_alloc(e, &e.DZ1, (int64_t)e.Bp * nb1))) return rc;
         if ((rc = dev_alloc(e, &e.d_loss, 2))) return rc;
         // inference chunk: keep Xchunk + Hchunk + Ochunk around 1.5 GB
         const int64_t per_row = (e.PT + nb1 + 2 * nb2) * (int64_t)sizeof(float);
@@ -346,7 +347,7 @@ int di_set_split(di_handle* h, const int32_t* train_rows, int64_t n_train, const
     free_split(e);
     const int64_t ldy = (int64_t)e.S * e.Op;
     e.n_train = n_train; e.n_test = n_test;
-    e.n_train_pad = round_up64(std::max<int64_t>(n_train, 1), e.B);
+    e.n_train_pad = std::max<int64_t>((n_train + e.B - 1) / e.B, 1) * e.Bp;
     e.n_test_pad = round_up64(std::max<int64_t>(n_test, 1), 128);
     int rc;
     if ((rc = dev_alloc(e, &e.d_train_rows, std::max<int64_t>(n_train, 1)))) return rc;
@@ -433,8 +434,8 @@ int di_train_step(di_handle* h, const int32_t* rows, int32_t nrows, int64_t step
     DI_CUDA(cudaMemcpyAsync(e.d_step_rows, rows, nrows * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
     DI_CUDA(cudaEventRecord(e.ev0, e.stream));
     DI_CUDA(cudaMemsetAsync(e.d_loss, 0, sizeof(double), e.stream));
-    launch_gather(e, e.d_step_rows, nullptr, 0, e.B, nrows, e.d_pred_cols, e.PT, e.Xstep);
-    launch_gather(e, e.d_step_rows, nullptr, 0, e.B, nrows, e.d_targ_cols, (int64_t)e.S * e.Op, e.Ystep);
+    launch_gather(e, e.d_step_rows, nullptr, 0, e.Bp, nrows, e.d_pred_cols, e.PT, e.Xstep);
+    launch_gather(e, e.d_step_rows, nullptr, 0, e.Bp, nrows, e.d_targ_cols, (int64_t)e.S * e.Op, e.Ystep);
     int rc = run_step(e, e.Xstep, e.Ystep, 0, nrows, step, 1);
     if (rc) return rc;
     DI_CUDA(cudaEventRecord(e.ev1, e.stream));
@@ -470,11 +471,11 @@ int di_train_epoch(di_handle* h, const int32_t* perm, int64_t first_step, float*
     DI_CUDA(cudaEventRecord(e.ev0, e.stream));
     DI_CUDA(cudaMemsetAsync(e.d_loss, 0, 2 * sizeof(double), e.stream));
     // stage this epoch's visiting order: batch i is rows [i*B, (i+1)*B) of Xtr / Ytr
-    launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_pred_cols, e.PT, e.Xtr);
-    launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_targ_cols, ldy, e.Ytr);
+    launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_pred_cols, e.PT, e.Xtr, e.B, e.Bp);
+    launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_targ_cols, ldy, e.Ytr, e.B, e.Bp);
     int64_t step = first_step;
-    for (int64_t r0 = 0; r0 < e.n_train; r0 += e.B, ++step) {
-        const int n_valid = (int)std::min<int64_t>(e.B, e.n_train - r0);
+    for (int64_t i0 = 0, r0 = 0; i0 < e.n_train; i0 += e.B, r0 += e.Bp, ++step) {
+        const int n_valid = (int)std::min<int64_t>(e.B, e.n_train - i0);
         int rc = run_step(e, e.Xtr, e.Ytr, r0, n_valid, step, 0);
         if (rc) return rc;
     }
@@ -622,9 +623,9 @@ int di_debug_read(di_handle* h, const char* which, float* out, int64_t capacity_
     else if (!strcmp(which, "dz2")) { src = e.DZ2; pitch = (int64_t)e.S * e.Op; }
     else if (!strcmp(which, "dz1")) { src = e.DZ1; pitch = (int64_t)e.S * e.Hp; }
     else return fail(e, DI_ERR_ARG, "di_debug_read: unknown buffer");
-    if (capacity_floats < pitch * e.B) return fail(e, DI_ERR_ARG, "di_debug_read: buffer too small");
+    if (capacity_floats < pitch * e.Bp) return fail(e, DI_ERR_ARG, "di_debug_read: buffer too small");
     DI_CUDA(cudaSetDevice(e.cfg.device));
-    DI_CUDA(cudaMemcpyAsync(out, src, (size_t)pitch * e.B * sizeof(float), cudaMemcpyDeviceToHost, e.stream));
+    DI_CUDA(cudaMemcpyAsync(out, src, (size_t)pitch * e.Bp * sizeof(float), cudaMemcpyDeviceToHost, e.stream));
     *ld = pitch;
     return sync_check(e);
 }

@@ -34,7 +34,7 @@ struct StepArgs {
 
 struct Engine {
     di_config cfg{};
-    int S = 0, H = 0, O = 0, B = 0, Hp = 0, Op = 0;
+    int S = 0, H = 0, O = 0, B = 0, Bp = 0, Hp = 0, Op = 0;
     std::vector<int> P, Pp, gid;
     std::vector<int64_t> coff;
     int64_t PT = 0;                 // sum of padded predictor counts
@@ -86,10 +86,14 @@ struct Engine {
 };
 
 // ---- staging ------------------------------------------------------------------------------------------------
-// out[i][j] = norm[row(i)][cols[j]] for i < n_valid and cols[j] >= 0, else 0;  row(i) = rows[perm ? perm[i] : i]
-// (rows == nullptr: row(i) = first_row + i)
+// out[i][j] = norm[row(src(i))][cols[j]] when src(i) is valid and cols[j] >= 0, else 0, for i in [0, n_out);
+//   row(k) = rows[perm ? perm[k] : k]   (rows == nullptr: row(k) = first_row + k)
+//   batch == 0: src(i) = i, valid iff i < n_valid
+//   batch  > 0: output rows come in groups of batch_pitch holding `batch` source rows each (the per-step batches
+//               of the training matrices): src(i) = (i / batch_pitch) * batch + i % batch_pitch, valid iff
+//               i % batch_pitch < batch and src(i) < n_valid
 void launch_gather(Engine& e, const int32_t* rows, const int32_t* perm, int64_t first_row, int64_t n_out,
-                   int64_t n_valid, const int32_t* cols, int64_t width, float* out);
+                   int64_t n_valid, const int32_t* cols, int64_t width, float* out, int batch = 0, int batch_pitch = 0);
 
 // ---- fp32 CUDA-core path (kernels_simt.cu) -------------------------------------------------------------------
 void simt_train_step(Engine& e, const StepArgs& a);

@@ -216,10 +216,17 @@ __global__ void __launch_bounds__(NT) simt_gemm(GemmParams p) {
 __global__ void gather_kernel(const float* __restrict__ norm, int64_t G, const int32_t* __restrict__ rows,
                               const int32_t* __restrict__ perm, int64_t first_row, int64_t n_out,
                               int64_t n_valid, const int32_t* __restrict__ cols, int64_t width,
-                              float* __restrict__ out) {
-    for (int64_t i = blockIdx.y; i < n_out; i += gridDim.y) {
-        float* dst = out + i * width;
-        if (i >= n_valid) {
+                              float* __restrict__ out, int batch, int batch_pitch) {
+    for (int64_t io = blockIdx.y; io < n_out; io += gridDim.y) {
+        float* dst = out + io * width;
+        int64_t i = io;
+        bool valid = io < n_valid;
+        if (batch > 0) {
+            const int64_t r = io % batch_pitch;
+            i = (io / batch_pitch) * batch + r;
+            valid = r < batch && i < n_valid;
+        }
+        if (!valid) {
             for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < width; j += (int64_t)gridDim.x * blockDim.x)
                 dst[j] = 0.f;
             continue;
@@ -268,11 +275,12 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 }  // namespace
 
 void launch_gather(Engine& e, const int32_t* rows, const int32_t* perm, int64_t first_row, int64_t n_out,
-                   int64_t n_valid, const int32_t* cols, int64_t width, float* out) {
+                   int64_t n_valid, const int32_t* cols, int64_t width, float* out, int batch, int batch_pitch) {
     if (n_out <= 0 || width <= 0) return;
     KernelTimer t(e, "gather");
     dim3 grid((unsigned)std::min<int64_t>((width + 255) / 256, 64), (unsigned)std::min<int64_t>(n_out, 16384));
-    gather_kernel<<<grid, 256, 0, e.stream>>>(e.d_norm, e.G, rows, perm, first_row, n_out, n_valid, cols, width, out);
+    gather_kernel<<<grid, 256, 0, e.stream>>>(e.d_norm, e.G, rows, perm, first_row, n_out, n_valid, cols, width, out,
+                                              batch, batch_pitch);
     count_launch(e, "gather");
 }
 
@@ -280,7 +288,7 @@ void launch_bias_adam(Engine& e, const AdamParams& adam) {
     KernelTimer t(e, "bias");
     const int64_t n2 = (int64_t)e.S * e.Op, n1 = (int64_t)e.S * e.Hp;
     const int64_t n = n1 + n2;
-    bias_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e.stream>>>(e.DZ2, e.DZ1, e.B, n2, n1, e.b2, e.mb2, e.vb2,
+    bias_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e.stream>>>(e.DZ2, e.DZ1, e.Bp, n2, n1, e.b2, e.mb2, e.vb2,
                                                                         e.b1, e.mb1, e.vb1, adam);
     count_launch(e, "bias");
 }
@@ -289,11 +297,11 @@ void simt_train_step(Engine& e, const StepArgs& a) {
     GemmParams p = base_params(e);
     p.X = a.X; p.ldx = a.ldx; p.row0 = a.row0; p.Y = a.Y; p.ldy = a.ldy;
     p.Hact = e.Hact; p.DZ2 = e.DZ2; p.DZ1 = e.DZ1;
-    p.rows = e.B; p.n_valid = a.n_valid; p.training = 1; p.step = a.step;
+    p.rows = e.Bp; p.n_valid = a.n_valid; p.training = 1; p.step = a.step;
     p.keep_scale = p.drop_thresh ? 1.0f / (1.0f - e.cfg.dropout_rate) : 1.0f;
     p.inv_norm = 1.0f / ((float)a.n_valid * (float)e.O);
     p.loss = e.d_loss; p.adam = a.adam;
-    const int mb = cdiv(e.B, BM);
+    const int mb = cdiv(e.Bp, BM);
     { KernelTimer t(e, "fwd1");
       simt_gemm<OP_FWD1><<<dim3(cdiv(e.Hp, BN), mb, e.S), NT, 0, e.stream>>>(p); count_launch(e, "fwd1"); }
     { KernelTimer t(e, "fwd2");

@@ -1,12 +1,420 @@
-// tcgen05 / TMA path (DI_MATH_TF32) -- placeholder until the kernels land: creating a TF32 engine fails loudly.
+// tcgen05 / TMA path (DI_MATH_TF32): every GEMM of the training step and of inference runs on the 5th-generation
+// tensor cores (kind::tf32: fp32 operands read straight from HBM by TMA, truncated to TF32 by the tensor core, fp32
+// accumulation in TMEM), batched over sub-networks with blockIdx.z, with the layer-specific work in the epilogue:
+//
+//   FWD1  h    = dropout(relu(X W1 + b1))                                   A = W1 (MN-major)  B = X    (K-major)
+//   FWD2  yhat = softplus(h W2 + b2); wMSE; dz2; b2 <- Adam(sum_b dz2)       A = W2 (MN-major)  B = h    (K-major)
+//   BWD   dz1  = (dz2 W2^T) * relu/dropout mask; b1 <- Adam(sum_b dz1)       A = W2 (K-major)   B = dz2  (K-major)
+//   ADAM  W   <- Adam(in^T dout), dW never leaves TMEM/registers             A = dout (MN-major) B = in (MN-major)
+//         (ADAM2: in = h, dout = dz2, W = W2;  ADAM1: in = X, dout = dz1, W = W1)
+//
+// Orientation: the M dimension of every MMA (the 128 TMEM lanes) is the layer's OUTPUT feature index -- the
+// contiguous dimension of the Keras-layout weights W[in][out] and of every activation row.  One epilogue thread
+// therefore owns one feature: its bias is a scalar, the bias gradient is a private sum over the batch columns, one
+// Philox call yields the keep-bits of 4 consecutive batch rows, and every global access of a warp is 32 consecutive
+// floats (128 B, coalesced) with no shared-memory transpose.  The batch (or the cell tile at inference) is the MMA
+// N dimension, so B = 64 costs N = 64 rather than a half-empty M.
+//
+// Warp roles (192 threads): warps 0-3 epilogue (warp w reads TMEM lanes 32w..32w+31), warp 4 TMA producer,
+// warp 5 MMA issuer.  smem ring of 32-wide K slabs, full/empty mbarriers, one tmem_full barrier.
+#include <algorithm>
+
 #include "engine.h"
 #include "tc_common.cuh"
 
 namespace di {
-bool tc_available() { return false; }
-bool tc_init(Engine& e) { e.err = "DI_MATH_TF32 kernels are not built in this revision"; return false; }
-void tc_destroy(Engine&) {}
-bool tc_rebind(Engine&) { return true; }
-void tc_train_step(Engine&, const StepArgs&, int) {}
-void tc_forward(Engine&, int, int64_t, int64_t, int64_t, bool, float*, int64_t) {}
+
+using namespace tc;
+
+namespace {
+
+enum { TC_FWD1 = 0, TC_FWD2 = 1, TC_BWD = 2, TC_ADAM = 3 };
+
+constexpr int TILE_M = 128;              // TMEM lanes = output features per CTA
+constexpr int NTHREADS = 192;
+constexpr int MAX_STAGES = 4;
+constexpr uint32_t A_STAGE_BYTES = TILE_M * BLOCK_K * 4;       // 16 KB
+
+struct TcParams {
+    const SubnetDesc* desc;
+    int S, H, O, Hp, Op;
+    int n_cols;                 // UMMA N: batch rows (FWD*/BWD) or input-feature tile width (ADAM)
+    int tmem_cols;              // power of two >= n_cols
+    int stages;
+    int which;                  // ADAM: 1 = W1 (in = X, dout = dz1), 2 = W2 (in = h, dout = dz2)
+    int64_t row0;               // first row of the batch / cell tile group inside the B-operand tensor
+    int64_t rows_per_block_y;   // inference: blockIdx.y / m_tiles selects a cell tile of n_cols rows
+    int m_tiles;                // feature tiles per sub-network
+    // epilogue operands
+    const float* Y; int64_t ldy;                 // packed targets
+    float* Hact; int64_t ldh;                    // [rows][S*Hp]
+    float* DZ2; float* DZ1;                      // [Bp][S*Op], [Bp][S*Hp]
+    float *b1, *mb1, *vb1, *b2, *mb2, *vb2;
+    float *W, *mW, *vW;                          // ADAM target
+    float* out; int64_t ld_out;                  // inference output
+    double* loss;
+    int n_valid;                                 // real rows of the batch / chunk
+    int training;
+    uint32_t step; uint64_t seed; uint32_t drop_thresh; float keep_scale;
+    float inv_norm;
+    AdamParams adam;
+};
+
+__device__ __forceinline__ uint32_t idesc_for(int n_cols, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(NTHREADS, OP == TC_ADAM ? 3 : 2) tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                      const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+    constexpr bool A_MN = (OP != TC_BWD);
+    constexpr bool B_MN = (OP == TC_ADAM);
+
+    const int s = blockIdx.z;
+    const SubnetDesc d = p.desc[s];
+    const int m_tile = (OP == TC_ADAM) ? blockIdx.y : (int)(blockIdx.y % p.m_tiles);
+    const int row_tile = (OP == TC_ADAM) ? 0 : (int)(blockIdx.y / p.m_tiles);
+    const int m0 = m_tile * TILE_M;                       // first output feature of this CTA
+    const int n0 = (OP == TC_ADAM) ? blockIdx.x * p.n_cols : 0;   // ADAM: first input feature of this CTA
+    const int64_t row0 = p.row0 + (int64_t)row_tile * p.rows_per_block_y;
+
+    // geometry: coordinates into the two tensor maps and the K extent
+    int out_dim, in_dim, nkb;
+    int a_c0, a_c1, b_c0, b_c1;          // element coordinates of K block 0 (c0 = contiguous dim, c1 = row)
+    if constexpr (OP == TC_FWD1) {
+        out_dim = p.Hp; in_dim = d.Pp; nkb = d.Pp / BLOCK_K;
+        a_c0 = m0; a_c1 = (int)d.coff;                    // W1 [PT][Hp]: rows = k (predictor), cols = feature
+        b_c0 = (int)d.coff; b_c1 = (int)row0;             // X  [rows][PT]
+    } else if constexpr (OP == TC_FWD2) {
+        out_dim = p.Op; in_dim = p.Hp; nkb = p.Hp / BLOCK_K;
+        a_c0 = m0; a_c1 = s * p.Hp;                       // W2 [S*Hp][Op]
+        b_c0 = s * p.Hp; b_c1 = (int)row0;                // h  [rows][S*Hp]
+    } else if constexpr (OP == TC_BWD) {
+        out_dim = p.Hp; in_dim = p.Op; nkb = p.Op / BLOCK_K;
+        a_c0 = 0; a_c1 = s * p.Hp + m0;                   // W2 rows = hidden unit, k = output gene (contiguous)
+        b_c0 = s * p.Op; b_c1 = 0;                        // dz2 [Bp][S*Op]
+    } else {
+        if (p.which == 1) { out_dim = p.Hp; in_dim = d.Pp; a_c0 = s * p.Hp + m0; b_c0 = (int)d.coff + n0; b_c1 = (int)row0; }
+        else { out_dim = p.Op; in_dim = p.Hp; a_c0 = s * p.Op + m0; b_c0 = s * p.Hp + n0; b_c1 = 0; }
+        a_c1 = 0;
+        nkb = p.rows_per_block_y / BLOCK_K;               // ADAM: K = padded batch rows
+    }
+    if (m0 >= out_dim || n0 >= in_dim) return;            // whole tile is padding (uniform per CTA)
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t b_stage_bytes = (uint32_t)p.n_cols * BLOCK_K * 4;
+    const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ double red[4];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = p.stages;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { prefetch_tensormap(&mapA); prefetch_tensormap(&mapB); }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % stages;
+                if (kb >= stages) mbar_wait(&empty_bar[st], ((kb / stages) - 1) & 1);
+                uint8_t* sa = smem + (size_t)st * stage_bytes;
+                uint8_t* sb = sa + A_STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
+                if constexpr (A_MN) load_stage<true>(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K, TILE_M);
+                else tma_load_2d(sa, &mapA, &full_bar[st], a_c0 + kb * BLOCK_K, a_c1);
+                if constexpr (B_MN) load_stage<true>(sb, &mapB, &full_bar[st], b_c0, b_c1 + kb * BLOCK_K, p.n_cols);
+                else tma_load_2d(sb, &mapB, &full_bar[st], b_c0 + kb * BLOCK_K, b_c1);
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            const uint32_t idesc = idesc_for(p.n_cols, A_MN, B_MN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % stages;
+                mbar_wait(&full_bar[st], (kb / stages) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
+                    umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<B_MN>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                umma_commit(&empty_bar[st]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = output features m0+32w.. =====
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const int f = m0 + warp * 32 + lane;              // output feature of this thread
+        const bool f_ok = f < out_dim;
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        const int ncol = p.n_cols;
+
+        if constexpr (OP == TC_FWD1) {
+            const float bias = f_ok ? p.b1[(int64_t)s * p.Hp + f] : 0.f;
+            const bool drop = p.training && p.drop_thresh;
+            float* hrow = p.Hact + row0 * p.ldh + (int64_t)s * p.Hp + f;
+            for (int c = 0; c < ncol; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + c, v);
+                if (!f_ok) continue;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+                    if (drop) dropout_words((uint32_t)f, (uint32_t)((c >> 2) + q), (uint32_t)d.gid, p.step, p.seed, w);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float a = fmaxf(v[4 * q + i] + bias, 0.f);
+                        if (drop) a = (w[i] >= p.drop_thresh) ? a * p.keep_scale : 0.f;
+                        hrow[(int64_t)(c + 4 * q + i) * p.ldh] = a;
+                    }
+                }
+            }
+        } else if constexpr (OP == TC_FWD2) {
+            const int64_t bi = (int64_t)s * p.Op + f;
+            const float bias = f_ok ? p.b2[bi] : 0.f;
+            double part = 0.0;
+            float gsum = 0.f;
+            for (int c = 0; c < ncol; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + c, v);
+                if (!f_ok) continue;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int b = c + i;
+                    const float z = v[i] + bias;
+                    const float yhat = softplus_f(z);
+                    if (p.out) {
+                        if (b < p.n_valid - row_tile * ncol && f < p.O)
+                            p.out[((int64_t)row_tile * ncol + b) * p.ld_out + (int64_t)s * p.O + f] = yhat;
+                    }
+                    if (p.Y) {
+                        const float y = p.Y[(row0 + b) * p.ldy + bi];
+                        const float diff = y - yhat;
+                        part += (double)(y * diff * diff);
+                        if (p.training) {
+                            const float g = 2.0f * y * (yhat - y) * sigmoid_f(z) * p.inv_norm;
+                            p.DZ2[(int64_t)b * p.S * p.Op + bi] = g;
+                            gsum += g;
+                        }
+                    }
+                }
+            }
+            if (p.training && f_ok) adam_update(gsum, p.b2[bi], p.mb2[bi], p.vb2[bi], p.adam);
+            if (p.loss) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+                if (lane == 0) red[warp] = part;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 0) atomicAdd(p.loss, red[0] + red[1] + red[2] + red[3]);
+            }
+        } else if constexpr (OP == TC_BWD) {
+            const int64_t bi = (int64_t)s * p.Hp + f;
+            float gsum = 0.f;
+            for (int c = 0; c < ncol; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + c, v);
+                if (!f_ok) continue;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int64_t idx = (int64_t)(c + i) * p.S * p.Hp + bi;
+                    const float g = (p.Hact[idx] > 0.f) ? v[i] * p.keep_scale : 0.f;
+                    p.DZ1[idx] = g;
+                    gsum += g;
+                }
+            }
+            if (f_ok) adam_update(gsum, p.b1[bi], p.mb1[bi], p.vb1[bi], p.adam);
+        } else {
+            // W[(row_base + n0 + col)][f]: one weight row per accumulator column; lanes = consecutive floats
+            const int64_t row_base = (p.which == 1) ? d.coff : (int64_t)s * p.Hp;
+            const int ldw = out_dim;
+            const int ncols_ok = min(ncol, in_dim - n0);
+            for (int c = 0; c < ncols_ok; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + c, v);
+                if (!f_ok) continue;
+                // in_dim is a multiple of 32, so a 16-column group is either entirely valid or entirely padding
+                int64_t off = (row_base + n0 + c) * ldw + f;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {              // 4 weight rows at a time: 12 loads in flight per thread
+                    float w[4], m[4], vv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        w[i] = p.W[off + (int64_t)i * ldw]; m[i] = p.mW[off + (int64_t)i * ldw]; vv[i] = p.vW[off + (int64_t)i * ldw];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        adam_update(v[4 * g + i], w[i], m[i], vv[i], p.adam);
+                        p.W[off + (int64_t)i * ldw] = w[i]; p.mW[off + (int64_t)i * ldw] = m[i]; p.vW[off + (int64_t)i * ldw] = vv[i];
+                    }
+                    off += 4 * (int64_t)ldw;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct TcState {
+    // weights / step buffers (fixed for the life of the engine)
+    CUtensorMap W1_mn, W2_mn, W2_k;
+    CUtensorMap H_k, H_mn, DZ2_k, DZ2_mn, DZ1_mn;          // training activations [Bp][...]
+    CUtensorMap Xstep_k, Xstep_mn;
+    CUtensorMap Xchunk_k, Hchunk_k;                        // inference chunk
+    // staged train / test matrices (rebuilt by tc_rebind)
+    CUtensorMap Xtr_k, Xtr_mn, Xte_k;
+    bool have_split = false;
+    int smem_fwd_train = 0, smem_fwd_infer = 0, smem_adam = 0, smem_bwd = 0;
+};
+
+constexpr int INFER_TILE = 128;      // cells per CTA at inference (UMMA N)
+constexpr int ADAM_TILE = 128;       // input features per CTA in the weight-gradient kernels (UMMA N)
+
+int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+int smem_for(int n_cols, int stages) { return stages * (int)(A_STAGE_BYTES + n_cols * BLOCK_K * 4) + 1024; }
+
+TcParams base_params(Engine& e) {
+    TcParams p{};
+    p.desc = e.d_desc; p.S = e.S; p.H = e.H; p.O = e.O; p.Hp = e.Hp; p.Op = e.Op;
+    p.b1 = e.b1; p.mb1 = e.mb1; p.vb1 = e.vb1; p.b2 = e.b2; p.mb2 = e.mb2; p.vb2 = e.vb2;
+    p.seed = e.cfg.seed;
+    const double r = e.cfg.dropout_rate;
+    p.drop_thresh = r > 0.0 ? (uint32_t)(r * 4294967296.0) : 0u;
+    p.keep_scale = 1.0f;
+    return p;
+}
+
+template <int OP>
+void launch(Engine& e, const char* name, const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, int smem) {
+    KernelTimer t(e, name);
+    tc_kernel<OP><<<grid, NTHREADS, smem, e.stream>>>(a, b, p);
+    count_launch(e, name);
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+bool tc_available() { return true; }
+
+bool tc_init(Engine& e) {
+    if (e.Bp > 256) { e.err = "DI_MATH_TF32 supports batch sizes up to 256 (use math mode fp32)"; return false; }
+    if (!get_encode_fn()) { e.err = "cuTensorMapEncodeTiled is not available from this driver"; return false; }
+    auto* st = new TcState();
+    e.tc = st;
+    const uint64_t SH = (uint64_t)e.S * e.Hp, SO = (uint64_t)e.S * e.Op;
+    bool ok = true;
+    ok = ok && make_map_2d(&st->W1_mn, e.W1, e.PT, e.Hp, e.Hp, 32, true);
+    ok = ok && make_map_2d(&st->W2_mn, e.W2, SH, e.Op, e.Op, 32, true);
+    ok = ok && make_map_2d(&st->W2_k, e.W2, SH, e.Op, e.Op, TILE_M);
+    ok = ok && make_map_2d(&st->H_k, e.Hact, e.Bp, SH, SH, e.Bp);
+    ok = ok && make_map_2d(&st->H_mn, e.Hact, e.Bp, SH, SH, 32, true);
+    ok = ok && make_map_2d(&st->DZ2_k, e.DZ2, e.Bp, SO, SO, e.Bp);
+    ok = ok && make_map_2d(&st->DZ2_mn, e.DZ2, e.Bp, SO, SO, 32, true);
+    ok = ok && make_map_2d(&st->DZ1_mn, e.DZ1, e.Bp, SH, SH, 32, true);
+    ok = ok && make_map_2d(&st->Xstep_k, e.Xstep, e.Bp, e.PT, e.PT, e.Bp);
+    ok = ok && make_map_2d(&st->Xstep_mn, e.Xstep, e.Bp, e.PT, e.PT, 32, true);
+    ok = ok && make_map_2d(&st->Xchunk_k, e.Xchunk, e.chunk_rows, e.PT, e.PT, INFER_TILE);
+    ok = ok && make_map_2d(&st->Hchunk_k, e.Hchunk, e.chunk_rows, SH, SH, INFER_TILE);
+    if (!ok) { e.err = "cuTensorMapEncodeTiled failed"; return false; }
+    st->smem_fwd_train = smem_for(e.Bp, MAX_STAGES);
+    st->smem_fwd_infer = smem_for(INFER_TILE, MAX_STAGES);
+    st->smem_bwd = smem_for(e.Bp, MAX_STAGES);
+    st->smem_adam = smem_for(ADAM_TILE, std::min(MAX_STAGES, e.Bp / BLOCK_K));
+    const int fwd_max = std::max(st->smem_fwd_train, st->smem_fwd_infer);
+    cudaError_t ce = cudaFuncSetAttribute(tc_kernel<TC_FWD1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_max);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_kernel<TC_FWD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_max);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_kernel<TC_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->smem_bwd);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_kernel<TC_ADAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->smem_adam);
+    if (ce != cudaSuccess) { e.err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return false; }
+    return true;
+}
+
+void tc_destroy(Engine& e) {
+    delete static_cast<TcState*>(e.tc);
+    e.tc = nullptr;
+}
+
+bool tc_rebind(Engine& e) {
+    auto* st = static_cast<TcState*>(e.tc);
+    if (!st) return true;
+    bool ok = true;
+    ok = ok && make_map_2d(&st->Xtr_k, e.Xtr, e.n_train_pad, e.PT, e.PT, e.Bp);
+    ok = ok && make_map_2d(&st->Xtr_mn, e.Xtr, e.n_train_pad, e.PT, e.PT, 32, true);
+    ok = ok && make_map_2d(&st->Xte_k, e.Xte, e.n_test_pad, e.PT, e.PT, INFER_TILE);
+    st->have_split = ok;
+    if (!ok) e.err = "cuTensorMapEncodeTiled failed (staged matrices)";
+    return ok;
+}
+
+void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
+    auto* st = static_cast<TcState*>(e.tc);
+    const CUtensorMap& Xk = which_x == 0 ? st->Xtr_k : st->Xstep_k;
+    const CUtensorMap& Xmn = which_x == 0 ? st->Xtr_mn : st->Xstep_mn;
+    TcParams p = base_params(e);
+    p.n_cols = e.Bp; p.tmem_cols = pow2_cols(e.Bp); p.stages = MAX_STAGES;
+    p.row0 = a.row0; p.rows_per_block_y = 0;
+    p.Y = a.Y; p.ldy = a.ldy; p.Hact = e.Hact; p.ldh = (int64_t)e.S * e.Hp; p.DZ2 = e.DZ2; p.DZ1 = e.DZ1;
+    p.n_valid = a.n_valid; p.training = 1; p.step = a.step;
+    p.keep_scale = p.drop_thresh ? 1.0f / (1.0f - e.cfg.dropout_rate) : 1.0f;
+    p.inv_norm = 1.0f / ((float)a.n_valid * (float)e.O);
+    p.loss = e.d_loss; p.adam = a.adam;
+    const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
+
+    TcParams p1 = p; p1.m_tiles = mh;
+    { TcParams q = p1; q.Hact = e.Hact - a.row0 * q.ldh;      // the kernel indexes Hact by row0 + b; training h starts at 0
+      launch<TC_FWD1>(e, "fwd1", st->W1_mn, Xk, q, dim3(1, mh, e.S), st->smem_fwd_train); }
+    { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
+      launch<TC_FWD2>(e, "fwd2", st->W2_mn, st->H_k, q, dim3(1, mo, e.S), st->smem_fwd_train); }
+    { TcParams q = p1; q.row0 = 0;
+      launch<TC_BWD>(e, "bwd", st->W2_k, st->DZ2_k, q, dim3(1, mh, e.S), st->smem_bwd); }
+    const int adam_stages = std::min(MAX_STAGES, e.Bp / BLOCK_K);
+    { TcParams q = p; q.which = 2; q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.stages = adam_stages;
+      q.rows_per_block_y = e.Bp; q.row0 = 0; q.W = e.W2; q.mW = e.mW2; q.vW = e.vW2;
+      launch<TC_ADAM>(e, "adam2", st->DZ2_mn, st->H_mn, q, dim3(cdiv(e.Hp, ADAM_TILE), mo, e.S), st->smem_adam); }
+    { TcParams q = p; q.which = 1; q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.stages = adam_stages;
+      q.rows_per_block_y = e.Bp; q.row0 = a.row0; q.W = e.W1; q.mW = e.mW1; q.vW = e.vW1;
+      launch<TC_ADAM>(e, "adam1", st->DZ1_mn, Xmn, q, dim3(cdiv(e.maxPp, ADAM_TILE), mh, e.S), st->smem_adam); }
+}
+
+void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_valid, bool with_loss,
+                float* out, int64_t ld_out) {
+    auto* st = static_cast<TcState*>(e.tc);
+    const CUtensorMap& Xk = which_x == 2 ? st->Xte_k : st->Xchunk_k;
+    TcParams p = base_params(e);
+    p.n_cols = INFER_TILE; p.tmem_cols = INFER_TILE; p.stages = MAX_STAGES;
+    p.rows_per_block_y = INFER_TILE;
+    p.ldh = (int64_t)e.S * e.Hp;
+    p.n_valid = (int)n_valid; p.training = 0; p.drop_thresh = 0;
+    const int row_tiles = (int)(rows / INFER_TILE);
+    const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
+    // hidden activations of this pass live in Hchunk rows [0, rows)
+    { TcParams q = p; q.m_tiles = mh; q.row0 = row0; q.Hact = e.Hchunk - row0 * q.ldh;
+      launch<TC_FWD1>(e, "infer1", st->W1_mn, Xk, q, dim3(1, mh * row_tiles, e.S), st->smem_fwd_infer); }
+    { TcParams q = p; q.m_tiles = mo; q.row0 = 0;
+      if (with_loss) { q.Y = e.Yte + row0 * (int64_t)e.S * e.Op; q.ldy = (int64_t)e.S * e.Op; q.loss = e.d_loss + 1; }
+      q.out = out; q.ld_out = ld_out;
+      launch<TC_FWD2>(e, "infer2", st->W2_mn, st->Hchunk_k, q, dim3(1, mo * row_tiles, e.S), st->smem_fwd_infer); }
+}
+
 }  // namespace di

@@ -1,13 +1,16 @@
 // sm_100a building blocks used by kernels_tc.cu: mbarrier, TMA (cp.async.bulk.tensor), TMEM allocation,
 // tcgen05.mma (kind::tf32) with shared-memory matrix descriptors, tcgen05.ld.  Inline PTX only.
 //
-// Shared-memory operand layouts (fp32/tf32 elements, 128-byte swizzle, tiles written by TMA):
-//   K-major  operand (K contiguous in memory):  one TMA box = [rows = MN extent][32 elements = 128 B];
-//            8-row groups are 1024 B apart (SBO); one MMA (K = 8) reads 32 B of every row, so successive
-//            MMAs inside the 128-byte atom advance the descriptor start address by 32 B.
-//   MN-major operand (M or N contiguous in memory): one TMA box = [rows = K extent][32 elements along MN];
-//            boxes for successive 32-element MN chunks are `box bytes` apart (LBO); one MMA (K = 8) reads one
-//            8-row group = 1024 B, so successive MMAs advance the start address by 1024 B (SBO = 1024).
+// Shared-memory operand layouts (fp32/tf32 elements, tiles written by TMA, verified bit-exact by umma_probe.cu):
+//   K-major  operand (K contiguous in memory):  one TMA box = [rows = MN extent][32 elements = 128 B], 128-byte
+//            swizzle (16-byte chunks); 8-row groups are 1024 B apart (SBO); one MMA (K = 8) reads 32 B of every
+//            row, so successive MMAs inside the 128-byte atom advance the descriptor start address by 32 B.
+//   MN-major operand (M or N contiguous in memory): one TMA box = [rows = K extent][32 elements along MN].
+//            For 32-bit operands the tensor core accepts only the "128-byte swizzle with 32-byte atomicity"
+//            layout here (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, descriptor layout type 1): the atom is
+//            32 MN elements x 4 K rows (512 B), 32-byte chunks XOR-ed with (row & 3).  Groups of 4 K rows are
+//            512 B apart (SBO), successive 32-element MN chunks one box apart (LBO = box bytes); one MMA (K = 8)
+//            reads two atoms = 1024 B, so successive MMAs advance the start address by 1024 B.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -93,17 +96,19 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------- descriptors
-constexpr uint32_t SWIZZLE_128B = 2;
+constexpr uint32_t SWIZZLE_128B = 2;            // 128-byte swizzle, 16-byte atomicity (K-major operands)
+constexpr uint32_t SWIZZLE_128B_BASE32B = 1;    // 128-byte swizzle, 32-byte atomicity (MN-major 32-bit operands)
 
 // Shared-memory matrix descriptor (sm_100 format: 14-bit address/LBO/SBO fields in 16-byte units, version 1
 // at bit 46, swizzle mode at bits 61..63).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = SWIZZLE_128B) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)SWIZZLE_128B << 61;
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 
@@ -145,8 +150,8 @@ __device__ __forceinline__ void load_stage(uint8_t* smem, const CUtensorMap* map
 // descriptor of the kstep-th (0..3) K=8 slice of a stage
 template <bool MN_MAJOR>
 __device__ __forceinline__ uint64_t stage_desc(uint32_t saddr, int kstep) {
-    if constexpr (MN_MAJOR) return make_smem_desc(saddr + kstep * 1024, MN_BOX_BYTES, 1024);
-    else return make_smem_desc(saddr + kstep * UMMA_K * 4, 16, 1024);
+    if constexpr (MN_MAJOR) return make_smem_desc(saddr + kstep * 1024, MN_BOX_BYTES, 512, SWIZZLE_128B_BASE32B);
+    else return make_smem_desc(saddr + kstep * UMMA_K * 4, 16, 1024, SWIZZLE_128B);
 }
 
 // 16 consecutive fp32 accumulator columns of this thread's TMEM lane (warp w reads lanes 32*(w%4) .. +31)
@@ -184,7 +189,9 @@ inline EncodeTiledFn get_encode_fn() {
 
 // fp32 row-major [rows][cols] with row pitch `pitch` floats; box = 32 floats (128 B, the swizzle span) x box_rows.
 // Out-of-bounds parts of a box are filled with zeros, which is what lets ragged K / M / N tails work.
-inline bool make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
+// mn_major selects the swizzle an MN-major 32-bit operand needs (32-byte atomicity), see the header comment.
+inline bool make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows,
+                        bool mn_major = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {cols, rows};
@@ -192,7 +199,9 @@ inline bool make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint
     cuuint32_t box[2] = {32, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }

@@ -11,7 +11,7 @@ using namespace di::tc;
 
 constexpr int M = 128, N = 64, K = 64;
 
-struct Over { int lbo, sbo, adv; };
+struct Over { int lbo, sbo, adv, type; };
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
         const uint32_t idesc = make_idesc_tf32(M, N, A_MN, B_MN);
         for (int kb = 0; kb < 2; ++kb)
             for (int j = 0; j < 4; ++j) {
-                const uint64_t da = make_smem_desc(smem_u32(sA + kb * 16384) + j * oa.adv, oa.lbo, oa.sbo);
-                const uint64_t db = make_smem_desc(smem_u32(sB + kb * 8192) + j * ob.adv, ob.lbo, ob.sbo);
+                const uint64_t da = make_smem_desc(smem_u32(sA + kb * 16384) + j * oa.adv, oa.lbo, oa.sbo, oa.type);
+                const uint64_t db = make_smem_desc(smem_u32(sB + kb * 8192) + j * ob.adv, ob.lbo, ob.sbo, ob.type);
                 umma_tf32(tm, da, db, idesc, (kb | j) ? 1u : 0u);
             }
         umma_commit(&mma_bar);
@@ -79,8 +79,8 @@ int run(Over oa, Over ob) {
     CK(cudaMemcpy(dB, Bg.data(), Bg.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(dD, 0xFF, D.size() * 4));
     CUtensorMap mA, mB;
-    bool ok = A_MN ? make_map_2d(&mA, dA, K, M, M, 32) : make_map_2d(&mA, dA, M, K, K, M);
-    ok = ok && (B_MN ? make_map_2d(&mB, dB, K, N, N, 32) : make_map_2d(&mB, dB, N, K, K, N));
+    bool ok = A_MN ? make_map_2d(&mA, dA, K, M, M, 32, true) : make_map_2d(&mA, dA, M, K, K, M);
+    ok = ok && (B_MN ? make_map_2d(&mB, dB, K, N, N, 32, true) : make_map_2d(&mB, dB, N, K, K, N));
     if (!ok) { printf("tensor map encode failed\n"); return 2; }
     const int smem = 2 * 16384 + 2 * 8192 + 1024;
     CK(cudaFuncSetAttribute(probe<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -90,17 +90,17 @@ int run(Over oa, Over ob) {
     CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
     int bad = 0; double maxerr = 0;
     for (int i = 0; i < M * N; ++i) { double e = fabs((double)D[i] - Dref[i]); if (!(e == 0)) ++bad; if (e > maxerr) maxerr = e; }
-    printf("a_mn=%d b_mn=%d A(lbo=%d sbo=%d adv=%d) B(lbo=%d sbo=%d adv=%d): mismatches=%d/%d maxerr=%g  D[0..3]=%g %g %g %g ref=%g %g %g %g\n",
-           (int)A_MN, (int)B_MN, oa.lbo, oa.sbo, oa.adv, ob.lbo, ob.sbo, ob.adv, bad, M * N, maxerr,
+    printf("a_mn=%d b_mn=%d A(lbo=%d sbo=%d adv=%d type=%d) B(lbo=%d sbo=%d adv=%d type=%d): mismatches=%d/%d maxerr=%g  D[0..3]=%g %g %g %g ref=%g %g %g %g\n",
+           (int)A_MN, (int)B_MN, oa.lbo, oa.sbo, oa.adv, oa.type, ob.lbo, ob.sbo, ob.adv, ob.type, bad, M * N, maxerr,
            D[0], D[1], D[2], D[3], Dref[0], Dref[1], Dref[2], Dref[3]);
     return bad ? 1 : 0;
 }
 
 int main(int argc, char** argv) {
     const int a_mn = argc > 1 ? atoi(argv[1]) : 0, b_mn = argc > 2 ? atoi(argv[2]) : 0;
-    Over oa = a_mn ? Over{(int)MN_BOX_BYTES, 1024, 1024} : Over{16, 1024, 32};
-    Over ob = b_mn ? Over{(int)MN_BOX_BYTES, 1024, 1024} : Over{16, 1024, 32};
-    if (argc > 8) { oa = Over{atoi(argv[3]), atoi(argv[4]), atoi(argv[5])}; ob = Over{atoi(argv[6]), atoi(argv[7]), atoi(argv[8])}; }
+    Over oa = a_mn ? Over{(int)MN_BOX_BYTES, 512, 1024, (int)SWIZZLE_128B_BASE32B} : Over{16, 1024, 32, (int)SWIZZLE_128B};
+    Over ob = b_mn ? Over{(int)MN_BOX_BYTES, 512, 1024, (int)SWIZZLE_128B_BASE32B} : Over{16, 1024, 32, (int)SWIZZLE_128B};
+    if (argc > 8) { oa.lbo = atoi(argv[3]); oa.sbo = atoi(argv[4]); oa.adv = atoi(argv[5]); ob.lbo = atoi(argv[6]); ob.sbo = atoi(argv[7]); ob.adv = atoi(argv[8]); }
     if (!a_mn && !b_mn) return run<false, false>(oa, ob);
     if (a_mn && !b_mn) return run<true, false>(oa, ob);
     if (!a_mn && b_mn) return run<false, true>(oa, ob);

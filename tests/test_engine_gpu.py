@@ -27,6 +27,7 @@ def modes():
 
 
 def make_problem(n_cells, n_genes, n_pred, O, seed):
+    n_genes = max(n_genes, len(n_pred) * O + max(n_pred) + 16)       # room for disjoint targets and predictors
     rng = np.random.default_rng(seed)
     lam = rng.gamma(0.6, 3.0, size=(1, n_genes)) * rng.gamma(2.0, 0.5, size=(n_cells, 1))
     norm = np.log1p(rng.poisson(lam)).astype(np.float32)
@@ -174,6 +175,44 @@ def test_fit_early_stopping_and_keras_adapters(mode):
     assert len(parts) == 2 and parts[0].shape == (20, O)
     assert rel_err(np.hstack(parts), np.hstack(ref.forward(Xte))) < (2e-4 if mode == "fp32" else 3e-2)
     eng.close()
+
+
+def test_tf32_tensor_core_rounding_model():
+    """kind::tf32 reads fp32 operands and drops the low 13 mantissa bits; the oracle in operand-truncation mode
+    must track the tensor-core result much more closely than the plain fp32 oracle does."""
+    if "tf32" not in modes():
+        pytest.skip("tf32 kernels not built")
+    n_pred, H, O, B = [600, 555], 256, 512, 64
+    norm, pred_idx, targ_idx = make_problem(256, 2400, n_pred, O, seed=11)
+    eng, ref32 = pair(n_pred, H, O, B, "tf32")
+    _, ref_tr = pair(n_pred, H, O, B, "fp32", oracle_round="tf32")
+    _.close()
+    eng.set_data(norm, pred_idx, targ_idx)
+    X, _y = stage(norm, pred_idx, targ_idx, np.arange(256))
+    got = eng.predict()
+    err32 = rel_err(got, np.hstack(ref32.forward(X)))
+    err_tr = rel_err(got, np.hstack(ref_tr.forward(X)))
+    print("tf32 forward: max rel err vs fp32 oracle {:.2e}, vs truncating oracle {:.2e}".format(err32, err_tr))
+    assert err32 < FWD_TOL["tf32"]
+    assert err_tr < 2e-4
+    eng.close()
+
+
+def test_odd_batch_size_is_padded_per_batch():
+    """batch_size 50 (not a multiple of 32): batches are staged at a padded pitch; results still match the oracle."""
+    for mode in modes():
+        n_pred, H, O, B = [45, 38], 24, 32, 50
+        norm, pred_idx, targ_idx = make_problem(180, 500, n_pred, O, seed=12)
+        eng, ref = pair(n_pred, H, O, B, mode, lr=5e-4)
+        eng.set_data(norm, pred_idx, targ_idx)
+        train_rows, test_rows = np.arange(170, dtype=np.int32), np.arange(170, 180, dtype=np.int32)   # 3*50 + 20
+        eng.set_split(train_rows, test_rows)
+        Xtr, Ytr = stage(norm, pred_idx, targ_idx, train_rows)
+        perm = epoch_permutation(7, 0, 170)
+        loss_ref, step = ref.train_epoch(Xtr, Ytr, perm, 0)
+        loss, _ = eng.train_epoch(perm)
+        assert step == 4 and loss == pytest.approx(loss_ref, rel=5e-5 if mode == "fp32" else 2e-2)
+        eng.close()
 
 
 def test_sharded_engines_reproduce_the_unsharded_model():
