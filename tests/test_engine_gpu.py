@@ -111,7 +111,12 @@ def test_single_step_matches_oracle(mode, n_pred, H, O, B, nrows):
         assert np.array_equal(hs == 0, inter[s]["h"].numpy() == 0) or mode != "fp32"
         assert rel_err(hs, inter[s]["h"].numpy()) < FWD_TOL[mode]
         assert rel_err(dz2[:n, s * Op:s * Op + O], inter[s]["dz2"].numpy()) < MOM_TOL[mode]
-        assert rel_err(dz1[:n, s * Hp:s * Hp + H], inter[s]["dz1"].numpy()) < MOM_TOL[mode]
+        # dz1 carries the relu mask [z1 > 0]: TF32 noise on a pre-activation next to zero flips the mask of that one
+        # unit (its dz1 is then the full dh instead of 0).  Compare where the masks agree; bound the flips.
+        d_gpu, d_ref = dz1[:n, s * Hp:s * Hp + H], inter[s]["dz1"].numpy()
+        agree = (hs > 0) == (inter[s]["h"].numpy() > 0)
+        assert agree.mean() > (1.0 if mode == "fp32" else 0.995)
+        assert rel_err(np.where(agree, d_gpu, 0), np.where(agree, d_ref, 0)) < MOM_TOL[mode]
         # padding rows (beyond the partial batch) and padding columns carry nothing
         assert not dz2[n:, s * Op:(s + 1) * Op].any() and not dz1[n:, s * Hp:(s + 1) * Hp].any()
         assert not dz2[:, s * Op + O:(s + 1) * Op].any() and not h[:, s * Hp + H:(s + 1) * Hp].any()
