@@ -255,7 +255,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("DI_BENCH_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--epochs", type=int, default=20, help="training epochs per step (fixed; no early stopping)")
-    ap.add_argument("--math", default=None, choices=["fp32", "tf32"])
+    ap.add_argument("--math", default=None, choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -432,7 +432,7 @@ def main():
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32" if math_mode == "fp32" else "tf32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32 (3-pass forward)"}[math_mode], "data": "synthetic",
             "config": {"workload": wl["desc"], "epochs_per_step": args.epochs, "batch_size": B,
                        "sub_networks": S_all, "hidden": HIDDEN, "sub_outputdim": OUT,
                        "predictors_per_subnet": [int(min(n_pred_all)), int(max(n_pred_all))],

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdeepimpute_b200.so")
 
-DI_MATH = {"fp32": 0, "tf32": 1}
+DI_MATH = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 
 
 class DiConfig(C.Structure):

@@ -111,7 +111,7 @@ int run_step(Engine& e, const float* X, const float* Y, int64_t row0, int n_vali
     StepArgs a;
     a.X = X; a.Y = Y; a.ldx = e.PT; a.ldy = (int64_t)e.S * e.Op; a.row0 = row0; a.n_valid = n_valid;
     a.step = (uint32_t)step; a.adam = adam_for_step(e, step);
-    if (e.cfg.math_mode == DI_MATH_TF32) tc_train_step(e, a, which_x);
+    if (e.cfg.math_mode != DI_MATH_FP32) tc_train_step(e, a, which_x);
     else simt_train_step(e, a);
     e.adam_t = step + 1;
     return DI_OK;
@@ -120,7 +120,7 @@ int run_step(Engine& e, const float* X, const float* Y, int64_t row0, int n_vali
 // forward over rows [row0, row0+rows) of a resident packed matrix; rows is a multiple of 128
 void run_forward(Engine& e, int which_x, const float* X, const float* Y, int64_t row0, int64_t rows,
                  int64_t n_valid, float* out, int64_t ld_out) {
-    if (e.cfg.math_mode == DI_MATH_TF32) {
+    if (e.cfg.math_mode != DI_MATH_FP32) {
         tc_forward(e, which_x, row0, rows, n_valid, Y != nullptr, out, ld_out);
     } else {
         simt_forward(e, X + row0 * e.PT, e.PT, rows, n_valid, e.Hchunk,
@@ -151,7 +151,7 @@ int di_version(void) { return 100; }
 
 int di_math_mode_available(int32_t math_mode) {
     if (math_mode == DI_MATH_FP32) return 1;
-    if (math_mode == DI_MATH_TF32) return tc_available() ? 1 : 0;
+    if (math_mode == DI_MATH_TF32 || math_mode == DI_MATH_TF32X3) return tc_available() ? 1 : 0;
     return 0;
 }
 
@@ -162,7 +162,7 @@ int di_create(di_handle** out, const di_config* cfg, const int32_t* n_pred) {
     *out = nullptr;
     if (cfg->n_subnets <= 0 || cfg->hidden <= 0 || cfg->sub_outputdim <= 0 || cfg->batch_size <= 0 ||
         cfg->dropout_rate < 0.f || cfg->dropout_rate >= 1.f ||
-        (cfg->math_mode != DI_MATH_FP32 && cfg->math_mode != DI_MATH_TF32)) {
+        (cfg->math_mode != DI_MATH_FP32 && cfg->math_mode != DI_MATH_TF32 && cfg->math_mode != DI_MATH_TF32X3)) {
         g_create_err = "invalid di_config"; return DI_ERR_ARG;
     }
     for (int s = 0; s < cfg->n_subnets; ++s)
@@ -238,7 +238,7 @@ int di_create(di_handle** out, const di_config* cfg, const int32_t* n_pred) {
             DI_CUDA(cudaEventCreateWithFlags(&e.ev_pinned[i], cudaEventDisableTiming));
             DI_CUDA(cudaEventCreateWithFlags(&e.ev_fwd[i], cudaEventDisableTiming));
         }
-        if (cfg->math_mode == DI_MATH_TF32 && !tc_init(e)) return DI_ERR_CUDA;
+        if (cfg->math_mode != DI_MATH_FP32 && !tc_init(e)) return DI_ERR_CUDA;
         return sync_check(e);
     };
     int rc = body();
@@ -362,7 +362,7 @@ int di_set_split(di_handle* h, const int32_t* train_rows, int64_t n_train, const
     // held-out matrices are staged once; training matrices are re-gathered in shuffled order every epoch
     launch_gather(e, e.d_test_rows, nullptr, 0, e.n_test_pad, n_test, e.d_pred_cols, e.PT, e.Xte);
     launch_gather(e, e.d_test_rows, nullptr, 0, e.n_test_pad, n_test, e.d_targ_cols, ldy, e.Yte);
-    if (e.cfg.math_mode == DI_MATH_TF32 && !tc_rebind(e)) return DI_ERR_CUDA;
+    if (e.cfg.math_mode != DI_MATH_FP32 && !tc_rebind(e)) return DI_ERR_CUDA;
     return sync_check(e);
 }
 

@@ -88,10 +88,15 @@ __device__ __forceinline__ void softplus_sigmoid(float z, float& sp, float& sg) 
 }
 
 // ============================================================================================ FWD1 / FWD2 / BWD
-template <int OP>
+// X3 = error-compensated "3xTF32" products for the forward GEMMs: the tensor core truncates an fp32 operand a to
+// its upper 19 bits (a_hi); the epilogue warps, idle during the main loop, write the residual a_lo = a - a_hi of
+// every staged slab next to it (element-wise, so the swizzled layout carries over unchanged) and the MMA warp issues
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi into the same accumulator.  The dropped a_lo*b_lo term is 2^-20 relative, i.e.
+// fp32-level products on the tensor cores, at 3x the (negligible) MMA time and 2x the staging memory.
+template <int OP, bool X3>
 __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                         const __grid_constant__ CUtensorMap mapB,
-                                                         const __grid_constant__ CUtensorMap mapC, const TcParams p) {
+                                                                  const __grid_constant__ CUtensorMap mapB,
+                                                                  const __grid_constant__ CUtensorMap mapC, const TcParams p) {
     constexpr bool A_MN = (OP != TC_BWD);
 
     const int s = blockIdx.z;
@@ -123,17 +128,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t b_stage_bytes = (uint32_t)p.n_cols * BLOCK_K * 4;
-    const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+    const uint32_t hi_bytes = A_STAGE_BYTES + b_stage_bytes;           // what TMA writes per stage
+    const uint32_t stage_bytes = X3 ? 2 * hi_bytes : hi_bytes;         // X3: [A_hi | B_hi | A_lo | B_lo]
     const int stages = p.stages;
     const float* aux = reinterpret_cast<const float*>(smem + (size_t)stages * stage_bytes);
-    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar, aux_bar;
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], conv_bar[MAX_STAGES], tmem_full_bar, aux_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ double red[4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&conv_bar[i], 128); }
         mbar_init(&tmem_full_bar, 1);
         mbar_init(&aux_bar, 1);
         fence_barrier_init();
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
                 if (kb >= stages) mbar_wait(&empty_bar[st], ((kb / stages) - 1) & 1);
                 uint8_t* sa = smem + (size_t)st * stage_bytes;
                 uint8_t* sb = sa + A_STAGE_BYTES;
-                mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
+                mbar_arrive_expect_tx(&full_bar[st], hi_bytes);
                 if constexpr (A_MN) load_stage<true>(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K, TILE_M);
                 else tma_load_2d(sa, &mapA, &full_bar[st], a_c0 + kb * BLOCK_K, a_c1);
                 tma_load_2d(sb, &mapB, &full_bar[st], b_c0 + kb * BLOCK_K, b_c1);
@@ -169,13 +175,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
             const uint32_t idesc = idesc_for(p.n_cols, A_MN, false);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % stages;
-                mbar_wait(&full_bar[st], (kb / stages) & 1);
+                mbar_wait(X3 ? &conv_bar[st] : &full_bar[st], (kb / stages) & 1);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                 const uint32_t sb = sa + A_STAGE_BYTES;
+                if constexpr (X3) {
+                    const uint32_t sa_lo = sa + hi_bytes, sb_lo = sb + hi_bytes;
 #pragma unroll
-                for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
-                    umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                    for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
+                        umma_tf32(tmem, stage_desc<A_MN>(sa_lo, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                        umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb_lo, j), idesc, 1u);
+                        umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
+                        umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                }
                 umma_commit(&empty_bar[st]);
             }
             umma_commit(&tmem_full_bar);
@@ -187,6 +203,27 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
         const bool f_ok = f < out_dim;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
         const int ncol = p.n_cols;
+        if constexpr (X3) {
+            // residual pass: lo = a - trunc19(a) for every float of the slab TMA just delivered
+            const int nvec = (int)(hi_bytes / 16);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % stages;
+                mbar_wait(&full_bar[st], (kb / stages) & 1);
+                const float4* hi = reinterpret_cast<const float4*>(smem + (size_t)st * stage_bytes);
+                float4* lo = reinterpret_cast<float4*>(smem + (size_t)st * stage_bytes + hi_bytes);
+                for (int i = threadIdx.x; i < nvec; i += 128) {
+                    const float4 v = hi[i];
+                    float4 r;
+                    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    lo[i] = r;
+                }
+                fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(&conv_bar[st]);
+            }
+        }
         if (p.aux_cols > 0) mbar_wait(&aux_bar, 0);
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
@@ -424,13 +461,26 @@ struct TcState {
     // staged train / test matrices (rebuilt by tc_rebind)
     CUtensorMap Xtr_k, Xtr_mn, Xte_k, Ytr_aux;
     bool have_split = false;
-    int stages_train = 0, smem_train_aux = 0, smem_fwd1_train = 0, smem_infer = 0, smem_adam = 0;
+    struct Cfg { int stages = 0, smem = 0; };
+    Cfg fwd1_train, fwd2_train, bwd_train, infer;          // ring depth and dynamic shared memory per launch
+    int smem_adam = 0;
+    bool x3 = false;                                       // forward GEMMs error-compensated (DI_MATH_TF32X3)
     int aux_h = 0, aux_y = 0, wbox1 = 0, wbox2 = 0;
 };
 
 int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
-int smem_for(int n_cols, int stages, int aux_floats) {
-    return stages * (int)(A_STAGE_BYTES + n_cols * BLOCK_K * 4) + aux_floats * 4 + 1024;
+int smem_for(int n_cols, int stages, int aux_floats, bool x3) {
+    return stages * (x3 ? 2 : 1) * (int)(A_STAGE_BYTES + n_cols * BLOCK_K * 4) + aux_floats * 4 + 1024;
+}
+// deepest ring (<= MAX_STAGES) that still leaves room for two CTAs per SM; if even two stages do not fit in half an
+// SM, the deepest ring that fits in one
+TcState::Cfg pick_cfg(int n_cols, int aux_floats, bool x3) {
+    TcState::Cfg c;
+    for (int budget : {110 * 1024, 224 * 1024}) {
+        for (int s = MAX_STAGES; s >= 2; --s)
+            if (smem_for(n_cols, s, aux_floats, x3) <= budget) { c.stages = s; c.smem = smem_for(n_cols, s, aux_floats, x3); return c; }
+    }
+    return c;      // stages == 0: does not fit
 }
 
 TcParams base_params(Engine& e) {
@@ -444,11 +494,11 @@ TcParams base_params(Engine& e) {
     return p;
 }
 
-template <int OP>
+template <int OP, bool X3>
 void launch(Engine& e, const char* name, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
             const TcParams& p, dim3 grid, int smem) {
     KernelTimer t(e, name);
-    tc_kernel<OP><<<grid, NTHREADS, smem, e.stream>>>(a, b, c, p);
+    tc_kernel<OP, X3><<<grid, NTHREADS, smem, e.stream>>>(a, b, c, p);
     count_launch(e, name);
 }
 
@@ -490,24 +540,29 @@ bool tc_init(Engine& e) {
         ok = ok && make_map_plain(&st->W2_t[i], w2[i], SH, e.Op, e.Op, st->wbox2, AD_R);
     }
     if (!ok) { e.err = "cuTensorMapEncodeTiled failed"; return false; }
-    // shared-memory budgets: keep two CTAs per SM where possible (<= ~110 KB each)
+    // shared-memory budgets.  The side-operand tile (aux) is dropped for the compensated FWD2, whose doubled slabs
+    // would otherwise push it to one CTA per SM (its 4 x S CTAs are more than one CTA per SM can hold in one wave).
+    st->x3 = e.cfg.math_mode == DI_MATH_TF32X3;
     const int aux_floats = e.Bp * TILE_M;
-    st->stages_train = MAX_STAGES;
-    while (st->stages_train > 2 && smem_for(e.Bp, st->stages_train, aux_floats) > 110 * 1024) --st->stages_train;
-    st->smem_train_aux = smem_for(e.Bp, st->stages_train, aux_floats);
-    st->smem_fwd1_train = smem_for(e.Bp, st->stages_train, 0);
-    st->smem_infer = smem_for(INFER_TILE, 3, 0);
+    st->fwd1_train = pick_cfg(e.Bp, 0, st->x3);
+    st->fwd2_train = pick_cfg(e.Bp, st->x3 ? 0 : aux_floats, st->x3);
+    st->bwd_train = pick_cfg(e.Bp, aux_floats, false);
+    st->infer = pick_cfg(INFER_TILE, 0, st->x3);
     const int nkb = e.Bp / BLOCK_K;
     st->smem_adam = nkb * (int)(A_STAGE_BYTES + ADAM_TILE * BLOCK_K * 4) + AD_STAGES * 3 * AD_R * TILE_M * 4 + 1024;
-    if (st->smem_adam > 227 * 1024 || st->smem_train_aux > 227 * 1024) {
-        e.err = "DI_MATH_TF32: batch size needs more shared memory than one SM has (use math mode fp32)";
+    if (st->smem_adam > 227 * 1024 || !st->fwd1_train.stages || !st->fwd2_train.stages || !st->bwd_train.stages || !st->infer.stages) {
+        e.err = "tensor-core math modes: this batch size needs more shared memory than one SM has (use math mode fp32)";
         return false;
     }
-    const int fwd_max = std::max(std::max(st->smem_train_aux, st->smem_fwd1_train), st->smem_infer);
-    cudaError_t ce = cudaFuncSetAttribute(tc_kernel<TC_FWD1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_max);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_kernel<TC_FWD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_max);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_kernel<TC_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_max);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->smem_adam);
+    const int m1 = std::max(st->fwd1_train.smem, st->infer.smem), m2 = std::max(st->fwd2_train.smem, st->infer.smem);
+    cudaError_t ce = cudaSuccess;
+    auto set = [&](const void* fn, int bytes) {
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    set((const void*)tc_kernel<TC_FWD1, false>, m1); set((const void*)tc_kernel<TC_FWD1, true>, m1);
+    set((const void*)tc_kernel<TC_FWD2, false>, m2); set((const void*)tc_kernel<TC_FWD2, true>, m2);
+    set((const void*)tc_kernel<TC_BWD, false>, st->bwd_train.smem);
+    set((const void*)tc_adam_kernel, st->smem_adam);
     if (ce != cudaSuccess) { e.err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return false; }
     return true;
 }
@@ -537,7 +592,7 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
     const CUtensorMap& Xmn = which_x == 0 ? st->Xtr_mn : st->Xstep_mn;
     const CUtensorMap& Yaux = which_x == 0 ? st->Ytr_aux : st->Ystep_aux;
     TcParams p = base_params(e);
-    p.n_cols = e.Bp; p.tmem_cols = pow2_cols(e.Bp); p.stages = st->stages_train;
+    p.n_cols = e.Bp; p.tmem_cols = pow2_cols(e.Bp);
     p.row0 = a.row0; p.rows_per_block_y = 0;
     p.Y = a.Y; p.ldy = a.ldy; p.Hact = e.Hact; p.ldh = (int64_t)e.S * e.Hp; p.DZ2 = e.DZ2; p.DZ1 = e.DZ1;
     p.n_valid = a.n_valid; p.training = 1; p.step = a.step;
@@ -547,12 +602,17 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
     const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
 
     { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
-      launch<TC_FWD1>(e, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, e.S), st->smem_fwd1_train); }
+      q.stages = st->fwd1_train.stages;
+      if (st->x3) launch<TC_FWD1, true>(e, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, e.S), st->fwd1_train.smem);
+      else launch<TC_FWD1, false>(e, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, e.S), st->fwd1_train.smem); }
     { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
-      q.aux_cols = st->aux_y; q.aux_row0 = a.row0;
-      launch<TC_FWD2>(e, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, e.S), st->smem_train_aux); }
+      q.stages = st->fwd2_train.stages;
+      if (st->x3) launch<TC_FWD2, true>(e, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, e.S), st->fwd2_train.smem);
+      else { q.aux_cols = st->aux_y; q.aux_row0 = a.row0;
+             launch<TC_FWD2, false>(e, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, e.S), st->fwd2_train.smem); } }
     { TcParams q = p; q.m_tiles = mh; q.row0 = 0; q.aux_cols = st->aux_h; q.aux_row0 = 0;
-      launch<TC_BWD>(e, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, e.S), st->smem_train_aux); }
+      q.stages = st->bwd_train.stages;
+      launch<TC_BWD, false>(e, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, e.S), st->bwd_train.smem); }
     TcParams q = p;
     q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;
     { q.which = 2; q.row0 = 0; q.wbox = st->wbox2;
@@ -572,7 +632,7 @@ void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_va
     auto* st = static_cast<TcState*>(e.tc);
     const CUtensorMap& Xk = which_x == 2 ? st->Xte_k : st->Xchunk_k;
     TcParams p = base_params(e);
-    p.n_cols = INFER_TILE; p.tmem_cols = INFER_TILE; p.stages = 3;
+    p.n_cols = INFER_TILE; p.tmem_cols = INFER_TILE; p.stages = st->infer.stages;
     p.rows_per_block_y = INFER_TILE;
     p.ldh = (int64_t)e.S * e.Hp;
     p.n_valid = (int)n_valid; p.training = 0; p.drop_thresh = 0;
@@ -580,11 +640,13 @@ void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_va
     const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
     // hidden activations of this pass live in Hchunk rows [0, rows)
     { TcParams q = p; q.m_tiles = mh; q.row0 = row0; q.Hact = e.Hchunk - row0 * q.ldh;
-      launch<TC_FWD1>(e, "infer1", st->W1_mn, Xk, Xk, q, dim3(1, mh * row_tiles, e.S), st->smem_infer); }
+      if (st->x3) launch<TC_FWD1, true>(e, "infer1", st->W1_mn, Xk, Xk, q, dim3(1, mh * row_tiles, e.S), st->infer.smem);
+      else launch<TC_FWD1, false>(e, "infer1", st->W1_mn, Xk, Xk, q, dim3(1, mh * row_tiles, e.S), st->infer.smem); }
     { TcParams q = p; q.m_tiles = mo; q.row0 = 0;
       if (with_loss) { q.Y = e.Yte + row0 * (int64_t)e.S * e.Op; q.ldy = (int64_t)e.S * e.Op; q.loss = e.d_loss + 1; }
       q.out = out; q.ld_out = ld_out;
-      launch<TC_FWD2>(e, "infer2", st->W2_mn, st->Hchunk_k, st->Hchunk_k, q, dim3(1, mo * row_tiles, e.S), st->smem_infer); }
+      if (st->x3) launch<TC_FWD2, true>(e, "infer2", st->W2_mn, st->Hchunk_k, st->Hchunk_k, q, dim3(1, mo * row_tiles, e.S), st->infer.smem);
+      else launch<TC_FWD2, false>(e, "infer2", st->W2_mn, st->Hchunk_k, st->Hchunk_k, q, dim3(1, mo * row_tiles, e.S), st->infer.smem); }
 }
 
 }  // namespace di

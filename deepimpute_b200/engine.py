@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib
 
 
-DEFAULT_MATH = "tf32"
+DEFAULT_MATH = "tf32x3"
 
 
 class History:

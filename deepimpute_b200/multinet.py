@@ -65,7 +65,7 @@ def inspect_data(data):
 class MultiNet:
     """Drop-in for ``deepimpute.multinet.MultiNet`` (reference ``multinet.py:65-375``).
 
-    Extra keyword-only arguments (not in the reference): ``math_mode`` ("tf32" tensor-core kernels, default, or
+    Extra keyword-only arguments (not in the reference): ``math_mode`` ("tf32x3" tensor-core kernels, default; "tf32"; or
     "fp32" CUDA-core kernels), ``device`` (CUDA ordinal) and ``shard`` (a ``parallel.ShardContext``: this process
     trains only its share of the sub-networks and the per-epoch losses / predicted blocks are exchanged with the
     other ranks; see ``deepimpute_b200.parallel``).

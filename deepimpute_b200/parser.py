@@ -36,8 +36,9 @@ _FLAGS = [
                          help="'restore' keeps every positive raw value, 'max' keeps max(raw, imputed). "
                               "Default: restore")),
     # ---- not in the reference ----
-    (("--math",), dict(type=str, default=None, choices=["tf32", "fp32"],
-                       help="Arithmetic of the GPU engine: tf32 tensor cores (default) or fp32 CUDA cores.")),
+    (("--math",), dict(type=str, default=None, choices=["tf32x3", "tf32", "fp32"],
+                       help="Arithmetic of the GPU engine: tf32x3 = tensor cores with error-compensated forward "
+                            "products (default), tf32 = single-pass tensor cores, fp32 = CUDA cores.")),
 ]
 
 

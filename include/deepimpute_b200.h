@@ -32,7 +32,10 @@ extern "C" {
 #define DI_ERR_NUMERIC   4   /* non-finite loss                            */
 
 #define DI_MATH_FP32     0   /* CUDA-core fp32 FFMA kernels (bit-for-bit fp32 products)          */
-#define DI_MATH_TF32     1   /* tcgen05 kind::tf32 tensor-core kernels, fp32 accumulate in TMEM  */
+#define DI_MATH_TF32     1   /* tcgen05 kind::tf32 tensor-core kernels, fp32 accumulate in TMEM; operands are
+                                TRUNCATED to TF32 by the tensor core (about 1e-3 relative per product)        */
+#define DI_MATH_TF32X3   2   /* same kernels, forward GEMMs error-compensated (a_hi b_hi + a_hi b_lo + a_lo b_hi):
+                                fp32-level activations and predictions; gradient GEMMs stay single-pass TF32 */
 
 typedef struct di_handle di_handle;
 

@@ -72,27 +72,35 @@ def test_fit_predict_matches_oracle_at_fixed_epochs(test_counts):
     assert rel[zero].max() < 1e-3
 
 
-def test_tf32_fit_predict_tracks_oracle(test_counts):
-    """Same as above on the tensor-core path (TF32 operands): training trajectories drift apart slowly, so the bound
-    is statistical -- losses within 1 %, imputed values within 1e-2 relative for 99 % of the entries."""
+def test_tensor_core_modes_track_the_fp32_path(test_counts):
+    """The same fit on the tensor-core paths.  Measured on a B200 (5 epochs, test.csv, imputed zeros, relative to the
+    fp32 path which itself sits within 1e-3 of the oracle, see above):
+      tf32   (operands truncated by the tensor core)   median 2.6e-3, 99th pct 4.5e-2, max 8.8e-2
+      tf32x3 (compensated forward GEMMs, the default)   bounds asserted below
+    so single-pass TF32 does NOT meet the 1e-3 target of the north star and is offered as an opt-in only."""
     from deepimpute_b200 import _lib
-    if not _lib.load().di_math_mode_available(_lib.DI_MATH["tf32"]):
-        pytest.skip("tf32 kernels not built")
+    if not _lib.load().di_math_mode_available(_lib.DI_MATH["tf32x3"]):
+        pytest.skip("tensor-core kernels not built")
     raw = test_counts
     nets = {}
-    for mode in ("fp32", "tf32"):
+    for mode in ("fp32", "tf32", "tf32x3"):
         net = MultiNet(seed=1234, ncores=1, max_epochs=5, patience=100, verbose=0, math_mode=mode)
         net.fit(raw)
         nets[mode] = (net, net.predict(raw, policy="restore").values)
-    np.testing.assert_allclose(nets["tf32"][0].history["loss"], nets["fp32"][0].history["loss"], rtol=1e-2)
-    np.testing.assert_allclose(nets["tf32"][0].history["val_loss"], nets["fp32"][0].history["val_loss"], rtol=1e-2)
     zero = raw.values == 0
-    a, b = nets["tf32"][1][zero], nets["fp32"][1][zero]
-    rel = np.abs(a - b) / (np.abs(b) + 1e-3)
-    print("tf32 vs fp32 imputed values after 5 epochs: median rel {:.2e}, 99th pct {:.2e}, max {:.2e}".format(
-        np.median(rel), np.quantile(rel, 0.99), rel.max()))
-    assert np.quantile(rel, 0.99) < 1e-2
-    assert abs(nets["tf32"][0].test_metrics["correlation"] - nets["fp32"][0].test_metrics["correlation"]) < 2e-3
+    stats = {}
+    for mode in ("tf32", "tf32x3"):
+        a, b = nets[mode][1][zero], nets["fp32"][1][zero]
+        rel = np.abs(a - b) / (np.abs(b) + 1e-3)
+        stats[mode] = (np.median(rel), np.quantile(rel, 0.99), rel.max())
+        print("{} vs fp32 imputed values after 5 epochs: median rel {:.2e}, 99th pct {:.2e}, max {:.2e}".format(
+            mode, *stats[mode]))
+    np.testing.assert_allclose(nets["tf32"][0].history["loss"], nets["fp32"][0].history["loss"], rtol=1e-2)
+    np.testing.assert_allclose(nets["tf32x3"][0].history["loss"], nets["fp32"][0].history["loss"], rtol=1e-3)
+    np.testing.assert_allclose(nets["tf32x3"][0].history["val_loss"], nets["fp32"][0].history["val_loss"], rtol=1e-3)
+    assert stats["tf32"][1] < 0.1
+    assert stats["tf32x3"][1] < 1e-3 and stats["tf32x3"][0] < 2e-4
+    assert abs(nets["tf32x3"][0].test_metrics["correlation"] - nets["fp32"][0].test_metrics["correlation"]) < 1e-4
 
 
 def test_deepimpute_entry_point(tmp_path, test_counts):
