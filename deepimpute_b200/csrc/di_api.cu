@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -17,7 +18,18 @@ static thread_local std::string g_create_err;
 
 namespace di {
 
-void count_launch(Engine& e, const char*) { ++e.launches; }
+void count_launch(Engine& e, const char* name) {
+    ++e.launches;
+    // DEEPIMPUTE_B200_DEBUG_SYNC=1: wait for every kernel and name the one that failed (asynchronous errors are
+    // otherwise reported by whatever runtime call comes next)
+    static const bool debug_sync = [] { const char* v = getenv("DEEPIMPUTE_B200_DEBUG_SYNC"); return v && *v == '1'; }();
+    if (debug_sync) {
+        cudaError_t err = cudaStreamSynchronize(e.stream);
+        if (err == cudaSuccess) err = cudaGetLastError();
+        if (err != cudaSuccess) fprintf(stderr, "deepimpute_b200: kernel '%s' (launch %lld) failed: %s\n", name,
+                                        (long long)e.launches, cudaGetErrorString(err));
+    }
+}
 
 // Per-kernel timing: an event pair around every launch on e.stream, recorded without synchronising and resolved
 // at the next host sync (resolve_timers), so the kernels still run back to back while they are being timed.
@@ -98,6 +110,17 @@ int sync_check(Engine& e) {
     DI_CUDA(cudaStreamSynchronize(e.stream));
     DI_CUDA(cudaGetLastError());
     if (!e.pending_timers.empty()) resolve_timers(e);
+    if (e.cfg.math_mode != DI_MATH_FP32) {
+        const unsigned int w = tc_take_timeout_word();
+        if (w) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "tensor-core kernel gave up waiting on an mbarrier (tag %u, sub-network %u, "
+                     "block y %u, warp %u): results of this call are invalid", (w >> 24) & 0x7Fu, (w >> 12) & 0xFFFu,
+                     (w >> 4) & 0xFFu, w & 0xFu);
+            e.err = buf;
+            return DI_ERR_CUDA;
+        }
+    }
     return DI_OK;
 }
 

@@ -103,6 +103,7 @@ void simt_forward(Engine& e, const float* X, int64_t ldx, int64_t rows, int64_t 
                   const float* Y, int64_t ldy, float* out, int64_t ld_out);
 
 // ---- tcgen05 / TMA path (kernels_tc.cu) ----------------------------------------------------------------------
+unsigned int tc_take_timeout_word();   // kernels_tc.cu: non-zero if an mbarrier wait timed out since the last call
 bool tc_available();                // false while the tensor-core kernels are not part of the build
 bool tc_init(Engine& e);            // builds tensor maps; false + e.err on failure
 void tc_destroy(Engine& e);

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
         if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % stages;
-                if (kb >= stages) mbar_wait(&empty_bar[st], ((kb / stages) - 1) & 1);
+                if (kb >= stages) mbar_wait(&empty_bar[st], ((kb / stages) - 1) & 1, 2);
                 uint8_t* sa = smem + (size_t)st * stage_bytes;
                 uint8_t* sb = sa + A_STAGE_BYTES;
                 mbar_arrive_expect_tx(&full_bar[st], hi_bytes);
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
             const uint32_t idesc = idesc_for(p.n_cols, A_MN, false);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % stages;
-                mbar_wait(X3 ? &conv_bar[st] : &full_bar[st], (kb / stages) & 1);
+                mbar_wait(X3 ? &conv_bar[st] : &full_bar[st], (kb / stages) & 1, 3);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                 const uint32_t sb = sa + A_STAGE_BYTES;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
             const int nvec = (int)(hi_bytes / 16);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % stages;
-                mbar_wait(&full_bar[st], (kb / stages) & 1);
+                mbar_wait(&full_bar[st], (kb / stages) & 1, 1);
                 const float4* hi = reinterpret_cast<const float4*>(smem + (size_t)st * stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(smem + (size_t)st * stage_bytes + hi_bytes);
                 for (int i = threadIdx.x; i < nvec; i += 128) {
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
                 mbar_arrive(&conv_bar[st]);
             }
         }
-        if (p.aux_cols > 0) mbar_wait(&aux_bar, 0);
-        mbar_wait(&tmem_full_bar, 0);
+        if (p.aux_cols > 0) mbar_wait(&aux_bar, 0, 5);
+        mbar_wait(&tmem_full_bar, 0, 4);
         tc_fence_after();
 
         if constexpr (OP == TC_FWD1) {
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
             for (int c = 0; c < nchunks; ++c) {
                 const int st = c % AD_STAGES;
                 float* ws = wring + (size_t)st * 3 * tile_floats;
-                mbar_wait(&wdone[st], (c / AD_STAGES) & 1);      // all 128 epilogue threads updated this chunk
+                mbar_wait(&wdone[st], (c / AD_STAGES) & 1, 8);      // all 128 epilogue threads updated this chunk
                 const int32_t r = (int32_t)(row_base + n0 + c * AD_R);
                 tma_store_2d(&mapW, ws, m0, r);
                 tma_store_2d(&mapM, ws + tile_floats, m0, r);
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     } else if (warp == 5) {
         if (elect_one()) {
             const uint32_t idesc = idesc_for(p.n_cols, true, true);
-            mbar_wait(&ops_bar, 0);
+            mbar_wait(&ops_bar, 0, 6);
             tc_fence_after();
             for (int kb = 0; kb < nkb; ++kb) {
                 const uint32_t sa = smem_u32(sA + (size_t)kb * A_STAGE_BYTES);
@@ -422,14 +422,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
         const int fl = warp * 32 + lane;
         const bool f_ok = (m0 + fl) < out_dim;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-        mbar_wait(&tmem_full_bar, 0);
+        mbar_wait(&tmem_full_bar, 0, 4);
         tc_fence_after();
         for (int c = 0; c < nchunks; ++c) {
             const int st = c % AD_STAGES;
             float* ws = wring + (size_t)st * 3 * tile_floats;
             float g[AD_R];
             tmem_ld8(taddr + c * AD_R, g);
-            mbar_wait(&wfull[st], (c / AD_STAGES) & 1);
+            mbar_wait(&wfull[st], (c / AD_STAGES) & 1, 7);
             if (f_ok) {
 #pragma unroll
                 for (int r = 0; r < AD_R; ++r) {
@@ -507,6 +507,13 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 }  // namespace
 
 bool tc_available() { return true; }
+
+unsigned int tc_take_timeout_word() {
+    unsigned int w = 0;
+    if (cudaMemcpyFromSymbol(&w, tc::g_mbar_timeout, sizeof w) != cudaSuccess) return 0;
+    if (w) { const unsigned int zero = 0; cudaMemcpyToSymbol(tc::g_mbar_timeout, &zero, sizeof zero); }
+    return w;
+}
 
 bool tc_init(Engine& e) {
     if (e.Bp > 256) { e.err = "DI_MATH_TF32 supports batch sizes up to 256 (use math mode fp32)"; return false; }

@@ -60,17 +60,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug must neither hang the GPU nor kill the context.  After ~0.5 s the waiter records
+// who gave up (g_mbar_timeout: tag << 24 | blockIdx.z << 12 | blockIdx.y << 4 | warp) and carries on, so the kernel
+// terminates with garbage results; the host reads the word at its next synchronisation point and fails the call
+// with that information (di_api.cu: sync_check).
+__device__ unsigned int g_mbar_timeout = 0;
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, uint32_t tag) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
-            printf("deepimpute_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-                   blockIdx.z, threadIdx.x);
-            __trap();
+        if (clock64() - t0 > 1000000000ll) {
+            atomicCAS(&g_mbar_timeout, 0u, (tag << 24) | ((blockIdx.z & 0xFFFu) << 12) | ((blockIdx.y & 0xFFu) << 4) |
+                                               ((threadIdx.x >> 5) & 0xFu) | 0x80000000u);
+            return;
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity, tag);
 }
 
 // --------------------------------------------------------------------------------------------------- TMA
@@ -196,6 +203,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 }
 
 }  // namespace tc
+
+// host: 0 if no mbarrier wait has timed out since the last call, else the recorded word (and clears it)
+unsigned int tc_take_timeout_word();
 
 // ---------------------------------------------------------------------------------- host: tensor maps
 // cuTensorMapEncodeTiled is fetched through the runtime so that nothing links against libcuda.
