@@ -126,7 +126,7 @@ int sync_check(Engine& e) {
 
 void free_split(Engine& e) {
     dev_free(e.d_train_rows); dev_free(e.d_test_rows); dev_free(e.d_perm);
-    dev_free(e.Xtr); dev_free(e.Ytr); dev_free(e.Xte); dev_free(e.Yte);
+    dev_free(e.Xtr); dev_free(e.Ytr); dev_free(e.Xte); dev_free(e.Yte); dev_free(e.Xtr_lo);
     e.n_train = e.n_test = e.n_train_pad = e.n_test_pad = 0;
 }
 
@@ -244,6 +244,12 @@ int di_create(di_handle** out, const di_config* cfg, const int32_t* n_pred) {
         if ((rc = dev_alloc(e, &e.Hact, (int64_t)e.Bp * nb1))) return rc;
         if ((rc = dev_alloc(e, &e.DZ2, (int64_t)e.Bp * nb2))) return rc;
         if ((rc = dev_alloc(e, &e.DZ1, (int64_t)e.Bp * nb1))) return rc;
+        if (cfg->math_mode == DI_MATH_TF32X3) {
+            if ((rc = dev_alloc(e, &e.Hlo, (int64_t)e.Bp * nb1))) return rc;
+            if ((rc = dev_alloc(e, &e.DZ2lo, (int64_t)e.Bp * nb2))) return rc;
+            if ((rc = dev_alloc(e, &e.DZ1lo, (int64_t)e.Bp * nb1))) return rc;
+            if ((rc = dev_alloc(e, &e.Xstep_lo, (int64_t)e.Bp * e.PT))) return rc;
+        }
         if ((rc = dev_alloc(e, &e.d_loss, 2))) return rc;
         // inference chunk: keep Xchunk + Hchunk + Ochunk around 1.5 GB
         const int64_t per_row = (e.PT + nb1 + 2 * nb2) * (int64_t)sizeof(float);
@@ -279,7 +285,8 @@ void di_destroy(di_handle* h) {
     free_split(e);
     dev_free(e.d_desc); dev_free(e.d_norm); dev_free(e.d_pred_cols); dev_free(e.d_targ_cols);
     float** all[] = {&e.W1, &e.mW1, &e.vW1, &e.b1, &e.mb1, &e.vb1, &e.W2, &e.mW2, &e.vW2, &e.b2, &e.mb2, &e.vb2,
-                     &e.Xstep, &e.Ystep, &e.Hact, &e.DZ2, &e.DZ1, &e.Xchunk, &e.Hchunk, &e.Ochunk, &e.OchunkB};
+                     &e.Xstep, &e.Ystep, &e.Hact, &e.DZ2, &e.DZ1, &e.Xchunk, &e.Hchunk, &e.Ochunk, &e.OchunkB,
+                     &e.Hlo, &e.DZ2lo, &e.DZ1lo, &e.Xstep_lo};
     for (float** p : all) dev_free(*p);
     dev_free(e.d_step_rows); dev_free(e.d_chunk_rows); dev_free(e.d_loss);
     resolve_timers(e);
@@ -377,6 +384,7 @@ int di_set_split(di_handle* h, const int32_t* train_rows, int64_t n_train, const
     if ((rc = dev_alloc(e, &e.d_perm, std::max<int64_t>(n_train, 1)))) return rc;
     if ((rc = dev_alloc(e, &e.d_test_rows, std::max<int64_t>(n_test, 1)))) return rc;
     if ((rc = dev_alloc(e, &e.Xtr, e.n_train_pad * e.PT, false))) return rc;
+    if (e.cfg.math_mode == DI_MATH_TF32X3 && (rc = dev_alloc(e, &e.Xtr_lo, e.n_train_pad * e.PT, false))) return rc;
     if ((rc = dev_alloc(e, &e.Ytr, e.n_train_pad * ldy, false))) return rc;
     if ((rc = dev_alloc(e, &e.Xte, e.n_test_pad * e.PT, false))) return rc;
     if ((rc = dev_alloc(e, &e.Yte, e.n_test_pad * ldy, false))) return rc;
@@ -457,7 +465,7 @@ int di_train_step(di_handle* h, const int32_t* rows, int32_t nrows, int64_t step
     DI_CUDA(cudaMemcpyAsync(e.d_step_rows, rows, nrows * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
     DI_CUDA(cudaEventRecord(e.ev0, e.stream));
     DI_CUDA(cudaMemsetAsync(e.d_loss, 0, sizeof(double), e.stream));
-    launch_gather(e, e.d_step_rows, nullptr, 0, e.Bp, nrows, e.d_pred_cols, e.PT, e.Xstep);
+    launch_gather(e, e.d_step_rows, nullptr, 0, e.Bp, nrows, e.d_pred_cols, e.PT, e.Xstep, 0, 0, e.Xstep_lo);
     launch_gather(e, e.d_step_rows, nullptr, 0, e.Bp, nrows, e.d_targ_cols, (int64_t)e.S * e.Op, e.Ystep);
     int rc = run_step(e, e.Xstep, e.Ystep, 0, nrows, step, 1);
     if (rc) return rc;
@@ -494,7 +502,7 @@ int di_train_epoch(di_handle* h, const int32_t* perm, int64_t first_step, float*
     DI_CUDA(cudaEventRecord(e.ev0, e.stream));
     DI_CUDA(cudaMemsetAsync(e.d_loss, 0, 2 * sizeof(double), e.stream));
     // stage this epoch's visiting order: batch i is rows [i*B, (i+1)*B) of Xtr / Ytr
-    launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_pred_cols, e.PT, e.Xtr, e.B, e.Bp);
+    launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_pred_cols, e.PT, e.Xtr, e.B, e.Bp, e.Xtr_lo);
     launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_targ_cols, ldy, e.Ytr, e.B, e.Bp);
     int64_t step = first_step;
     for (int64_t i0 = 0, r0 = 0; i0 < e.n_train; i0 += e.B, r0 += e.Bp, ++step) {

@@ -60,6 +60,9 @@ struct Engine {
     float *Xstep = nullptr, *Ystep = nullptr;     // [B][PT], [B][S*Op]   explicit-batch step
     int32_t* d_step_rows = nullptr;               // [B]
     float *Hact = nullptr, *DZ2 = nullptr, *DZ1 = nullptr;
+    // DI_MATH_TF32X3 only: residual twins a_lo = a - trunc_tf32(a) of the operands of the weight-gradient GEMMs,
+    // written by the epilogue (h, dz2, dz1) or the staging gather (X) that produces the value itself
+    float *Hlo = nullptr, *DZ2lo = nullptr, *DZ1lo = nullptr, *Xtr_lo = nullptr, *Xstep_lo = nullptr;
 
     int64_t chunk_rows = 0;                       // inference chunk (multiple of 128)
     float *Xchunk = nullptr, *Hchunk = nullptr, *Ochunk = nullptr, *OchunkB = nullptr;
@@ -92,11 +95,14 @@ struct Engine {
 //   batch  > 0: output rows come in groups of batch_pitch holding `batch` source rows each (the per-step batches
 //               of the training matrices): src(i) = (i / batch_pitch) * batch + i % batch_pitch, valid iff
 //               i % batch_pitch < batch and src(i) < n_valid
+//   out_lo != nullptr: also writes the TF32 residual x - trunc_tf32(x) of every value to out_lo (same shape)
 void launch_gather(Engine& e, const int32_t* rows, const int32_t* perm, int64_t first_row, int64_t n_out,
-                   int64_t n_valid, const int32_t* cols, int64_t width, float* out, int batch = 0, int batch_pitch = 0);
+                   int64_t n_valid, const int32_t* cols, int64_t width, float* out, int batch = 0, int batch_pitch = 0,
+                   float* out_lo = nullptr);
 
 // ---- fp32 CUDA-core path (kernels_simt.cu) -------------------------------------------------------------------
 void simt_train_step(Engine& e, const StepArgs& a);
+void simt_adam_only(Engine& e, const StepArgs& a);   // W1/W2 <- Adam(exact fp32 dW); no bias update
 // forward for `rows` rows of X (multiple of 64): Hbuf [rows][S*Hp] scratch; if Y != nullptr accumulates the raw
 // validation sum into d_loss[1]; if out != nullptr writes yhat to out[rows][ld_out] (column s*O + o).
 void simt_forward(Engine& e, const float* X, int64_t ldx, int64_t rows, int64_t n_valid, float* Hbuf,

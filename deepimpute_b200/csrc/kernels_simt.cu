@@ -216,9 +216,10 @@ __global__ void __launch_bounds__(NT) simt_gemm(GemmParams p) {
 __global__ void gather_kernel(const float* __restrict__ norm, int64_t G, const int32_t* __restrict__ rows,
                               const int32_t* __restrict__ perm, int64_t first_row, int64_t n_out,
                               int64_t n_valid, const int32_t* __restrict__ cols, int64_t width,
-                              float* __restrict__ out, int batch, int batch_pitch) {
+                              float* __restrict__ out, int batch, int batch_pitch, float* __restrict__ out_lo) {
     for (int64_t io = blockIdx.y; io < n_out; io += gridDim.y) {
         float* dst = out + io * width;
+        float* dst_lo = out_lo ? out_lo + io * width : nullptr;
         int64_t i = io;
         bool valid = io < n_valid;
         if (batch > 0) {
@@ -227,15 +228,19 @@ __global__ void gather_kernel(const float* __restrict__ norm, int64_t G, const i
             valid = r < batch && i < n_valid;
         }
         if (!valid) {
-            for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < width; j += (int64_t)gridDim.x * blockDim.x)
+            for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < width; j += (int64_t)gridDim.x * blockDim.x) {
                 dst[j] = 0.f;
+                if (dst_lo) dst_lo[j] = 0.f;
+            }
             continue;
         }
         const int64_t r = rows ? (int64_t)rows[perm ? perm[i] : i] : first_row + i;
         const float* src = norm + r * G;
         for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < width; j += (int64_t)gridDim.x * blockDim.x) {
             const int32_t c = cols[j];
-            dst[j] = (c >= 0) ? __ldg(src + c) : 0.f;
+            const float v = (c >= 0) ? __ldg(src + c) : 0.f;
+            dst[j] = v;
+            if (dst_lo) dst_lo[j] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
         }
     }
 }
@@ -275,12 +280,13 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 }  // namespace
 
 void launch_gather(Engine& e, const int32_t* rows, const int32_t* perm, int64_t first_row, int64_t n_out,
-                   int64_t n_valid, const int32_t* cols, int64_t width, float* out, int batch, int batch_pitch) {
+                   int64_t n_valid, const int32_t* cols, int64_t width, float* out, int batch, int batch_pitch,
+                   float* out_lo) {
     if (n_out <= 0 || width <= 0) return;
     KernelTimer t(e, "gather");
     dim3 grid((unsigned)std::min<int64_t>((width + 255) / 256, 64), (unsigned)std::min<int64_t>(n_out, 16384));
     gather_kernel<<<grid, 256, 0, e.stream>>>(e.d_norm, e.G, rows, perm, first_row, n_out, n_valid, cols, width, out,
-                                              batch, batch_pitch);
+                                              batch, batch_pitch, out_lo);
     count_launch(e, "gather");
 }
 
@@ -313,6 +319,19 @@ void simt_train_step(Engine& e, const StepArgs& a) {
     { KernelTimer t(e, "adam1");
       simt_gemm<OP_ADAM1><<<dim3(cdiv(e.Hp, BN), cdiv(e.maxPp, BM), e.S), NT, 0, e.stream>>>(p); count_launch(e, "adam1"); }
     launch_bias_adam(e, a.adam);
+}
+
+// exact-fp32 weight updates only (dW on the CUDA cores + Adam); biases are left to the caller.  Used by the
+// tensor-core path as the reference implementation of its ADAM kernel in experiments.
+void simt_adam_only(Engine& e, const StepArgs& a) {
+    GemmParams p = base_params(e);
+    p.X = a.X; p.ldx = a.ldx; p.row0 = a.row0; p.Y = a.Y; p.ldy = a.ldy;
+    p.Hact = e.Hact; p.DZ2 = e.DZ2; p.DZ1 = e.DZ1;
+    p.rows = e.Bp; p.n_valid = a.n_valid; p.training = 1; p.step = a.step; p.adam = a.adam;
+    { KernelTimer t(e, "adam2");
+      simt_gemm<OP_ADAM2><<<dim3(cdiv(e.Op, BN), cdiv(e.Hp, BM), e.S), NT, 0, e.stream>>>(p); count_launch(e, "adam2"); }
+    { KernelTimer t(e, "adam1");
+      simt_gemm<OP_ADAM1><<<dim3(cdiv(e.Hp, BN), cdiv(e.maxPp, BM), e.S), NT, 0, e.stream>>>(p); count_launch(e, "adam1"); }
 }
 
 void simt_forward(Engine& e, const float* X, int64_t ldx, int64_t rows, int64_t n_valid, float* Hbuf,

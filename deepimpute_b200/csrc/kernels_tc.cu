@@ -23,6 +23,7 @@
 // Warp roles (192 threads): warps 0-3 epilogue (warp w reads TMEM lanes 32w..32w+31), warp 4 TMA producer,
 // warp 5 MMA issuer.  smem ring of 32-wide K slabs, full/empty mbarriers, one tmem_full barrier.
 #include <algorithm>
+#include <cstdlib>
 
 #include "engine.h"
 #include "tc_common.cuh"
@@ -63,6 +64,7 @@ struct TcParams {
     const float* Y; int64_t ldy;                 // packed targets
     float* Hact; int64_t ldh;                    // [rows][S*Hp]
     float* DZ2; float* DZ1;                      // [Bp][S*Op], [Bp][S*Hp]
+    float *Hlo, *DZ2lo, *DZ1lo;                  // TF32 residual twins of h / dz2 / dz1 (nullptr: not wanted)
     float *b1, *mb1, *vb1, *b2, *mb2, *vb2;
     float* out; int64_t ld_out;                  // inference output
     double* loss;
@@ -76,6 +78,11 @@ struct TcParams {
 __device__ __forceinline__ uint32_t idesc_for(int n_cols, bool a_mn, bool b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
            ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// residual of the tensor core's operand truncation: a - (a with the low 13 mantissa bits cleared)
+__device__ __forceinline__ float tf32_residual(float a) {
+    return a - __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
 }
 
 // softplus and sigmoid of z from one exponential (output layer, multinet.py:145, and its derivative)
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
             const float bias = f_ok ? p.b1[(int64_t)s * p.Hp + f] : 0.f;
             const bool drop = p.training && p.drop_thresh;
             float* hrow = p.Hact + row0 * p.ldh + (int64_t)s * p.Hp + f;
+            float* hlo = (p.training && p.Hlo) ? p.Hlo + (int64_t)s * p.Hp + f : nullptr;   // training h starts at row 0
             for (int c = 0; c < ncol; c += 16) {
                 float v[16];
                 tmem_ld16(taddr + c, v);
@@ -245,6 +253,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
                         float a = fmaxf(v[4 * q + i] + bias, 0.f);
                         if (drop) a = (w[i] >= p.drop_thresh) ? a * p.keep_scale : 0.f;
                         hrow[(int64_t)(c + 4 * q + i) * p.ldh] = a;
+                        if (hlo) hlo[(int64_t)(c + 4 * q + i) * p.ldh] = tf32_residual(a);
                     }
                 }
             }
@@ -280,6 +289,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
                         if (p.training) {
                             const float g = 2.0f * y[i] * (yhat - y[i]) * sg * p.inv_norm;
                             p.DZ2[(int64_t)b * p.S * p.Op + bi] = g;
+                            if (p.DZ2lo) p.DZ2lo[(int64_t)b * p.S * p.Op + bi] = tf32_residual(g);
                             gsum += g;
                         }
                     }
@@ -312,6 +322,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
                 for (int i = 0; i < 16; ++i) {
                     const float g = (h[i] > 0.f) ? v[i] * p.keep_scale : 0.f;
                     p.DZ1[(int64_t)(c + i) * p.S * p.Hp + bi] = g;
+                    if (p.DZ1lo) p.DZ1lo[(int64_t)(c + i) * p.S * p.Hp + bi] = tf32_residual(g);
                     gsum += g;
                 }
             }
@@ -327,8 +338,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
 // ============================================================================================ ADAM (weight update)
 // One CTA: dW tile [128 output features (lanes)] x [n_cols input features (columns)] = dout^T in, K = padded batch.
 // shared memory: operands (all K blocks at once) | ring of AD_STAGES x {w, m, v} x [AD_R rows][wbox floats]
+// X3: the error-compensated product needs dout_hi in_hi + dout_hi in_lo + dout_lo in_hi.  The residual twins already
+// exist in global memory (written by the kernels that produced dout / in), so the three terms are three
+// load -> MMA rounds through the SAME operand buffers: no second copy in shared memory, two CTAs per SM as before.
+template <bool X3>
 __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB,
+                                                              const __grid_constant__ CUtensorMap mapAlo,
+                                                              const __grid_constant__ CUtensorMap mapBlo,
                                                               const __grid_constant__ CUtensorMap mapW,
                                                               const __grid_constant__ CUtensorMap mapM,
                                                               const __grid_constant__ CUtensorMap mapV, const TcParams p) {
@@ -354,12 +371,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     const int wbox = p.wbox;
     const int tile_floats = AD_R * wbox;                  // one tensor, one chunk
     const uint32_t chunk_bytes = 3u * tile_floats * 4u;
-    __shared__ uint64_t ops_bar, tmem_full_bar, wfull[AD_STAGES], wdone[AD_STAGES];
+    __shared__ uint64_t ops_bar, mma_bar, tmem_full_bar, wfull[AD_STAGES], wdone[AD_STAGES];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        mbar_init(&ops_bar, 1); mbar_init(&tmem_full_bar, 1);
+        mbar_init(&ops_bar, 1); mbar_init(&mma_bar, 1); mbar_init(&tmem_full_bar, 1);
         for (int i = 0; i < AD_STAGES; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wdone[i], 128); }
         fence_barrier_init();
     }
@@ -382,12 +399,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     if (warp == 4) {
         // ===== TMA: operands, then the w/m/v ring (loads ahead of the epilogue, stores behind it) =====
         if (elect_one()) {
+            auto load_a = [&](const CUtensorMap* m) {
+                for (int kb = 0; kb < nkb; ++kb)
+                    load_stage<true>(sA + (size_t)kb * A_STAGE_BYTES, m, &ops_bar, a_c0, kb * BLOCK_K, TILE_M);
+            };
+            auto load_b = [&](const CUtensorMap* m) {
+                for (int kb = 0; kb < nkb; ++kb)
+                    load_stage<true>(sB + (size_t)kb * b_block_bytes, m, &ops_bar, b_c0, b_c1 + kb * BLOCK_K, p.n_cols);
+            };
             mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * (A_STAGE_BYTES + b_block_bytes));
-            for (int kb = 0; kb < nkb; ++kb) {
-                load_stage<true>(sA + (size_t)kb * A_STAGE_BYTES, &mapA, &ops_bar, a_c0, kb * BLOCK_K, TILE_M);
-                load_stage<true>(sB + (size_t)kb * b_block_bytes, &mapB, &ops_bar, b_c0, b_c1 + kb * BLOCK_K, p.n_cols);
-            }
+            load_a(&mapA); load_b(&mapB);                          // round 0: dout_hi, in_hi
             for (int c = 0; c < min(AD_STAGES, nchunks); ++c) load_chunk(c);
+            if constexpr (X3) {
+                mbar_wait(&mma_bar, 0, 9);                         // round 0 MMAs have read the buffers
+                mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * b_block_bytes);
+                load_b(&mapBlo);                                   // round 1: dout_hi (kept), in_lo
+                mbar_wait(&mma_bar, 1, 9);
+                mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * (A_STAGE_BYTES + b_block_bytes));
+                load_a(&mapAlo); load_b(&mapB);                    // round 2: dout_lo, in_hi
+            }
             for (int c = 0; c < nchunks; ++c) {
                 const int st = c % AD_STAGES;
                 float* ws = wring + (size_t)st * 3 * tile_floats;
@@ -407,14 +437,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     } else if (warp == 5) {
         if (elect_one()) {
             const uint32_t idesc = idesc_for(p.n_cols, true, true);
-            mbar_wait(&ops_bar, 0, 6);
-            tc_fence_after();
-            for (int kb = 0; kb < nkb; ++kb) {
-                const uint32_t sa = smem_u32(sA + (size_t)kb * A_STAGE_BYTES);
-                const uint32_t sb = smem_u32(sB + (size_t)kb * b_block_bytes);
+            constexpr int ROUNDS = X3 ? 3 : 1;
+            for (int round = 0; round < ROUNDS; ++round) {
+                mbar_wait(&ops_bar, round & 1, 6);
+                tc_fence_after();
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint32_t sa = smem_u32(sA + (size_t)kb * A_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(sB + (size_t)kb * b_block_bytes);
 #pragma unroll
-                for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
-                    umma_tf32(tmem, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                    for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
+                        umma_tf32(tmem, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (round | kb | j) ? 1u : 0u);
+                }
+                if (round + 1 < ROUNDS) umma_commit(&mma_bar);
             }
             umma_commit(&tmem_full_bar);
         }
@@ -454,6 +488,7 @@ struct TcState {
     // weights / step buffers (fixed for the life of the engine)
     CUtensorMap W1_mn, W2_mn, W2_k;
     CUtensorMap H_k, H_mn, DZ2_k, DZ2_mn, DZ1_mn;          // training activations [Bp][...]
+    CUtensorMap Hlo_mn, DZ2lo_mn, DZ1lo_mn, Xstep_lo_mn, Xtr_lo_mn;   // residual twins (x3)
     CUtensorMap H_aux;                                     // h tile for the BWD epilogue
     CUtensorMap Xstep_k, Xstep_mn, Ystep_aux;
     CUtensorMap Xchunk_k, Hchunk_k;                        // inference chunk
@@ -465,6 +500,7 @@ struct TcState {
     Cfg fwd1_train, fwd2_train, bwd_train, infer;          // ring depth and dynamic shared memory per launch
     int smem_adam = 0;
     bool x3 = false;                                       // forward GEMMs error-compensated (DI_MATH_TF32X3)
+    bool x3_bwd = false, simt_adam = false;                // experiments (DEEPIMPUTE_B200_EXPERIMENT bit 0 / bit 1)
     int aux_h = 0, aux_y = 0, wbox1 = 0, wbox2 = 0;
 };
 
@@ -538,6 +574,12 @@ bool tc_init(Engine& e) {
     ok = ok && make_map_2d(&st->Xstep_k, e.Xstep, e.Bp, e.PT, e.PT, e.Bp);
     ok = ok && make_map_2d(&st->Xstep_mn, e.Xstep, e.Bp, e.PT, e.PT, 32, true);
     ok = ok && make_map_plain(&st->Ystep_aux, e.Ystep, e.Bp, SO, SO, st->aux_y, e.Bp);
+    if (e.cfg.math_mode == DI_MATH_TF32X3) {
+        ok = ok && make_map_2d(&st->Hlo_mn, e.Hlo, e.Bp, SH, SH, 32, true);
+        ok = ok && make_map_2d(&st->DZ2lo_mn, e.DZ2lo, e.Bp, SO, SO, 32, true);
+        ok = ok && make_map_2d(&st->DZ1lo_mn, e.DZ1lo, e.Bp, SH, SH, 32, true);
+        ok = ok && make_map_2d(&st->Xstep_lo_mn, e.Xstep_lo, e.Bp, e.PT, e.PT, 32, true);
+    }
     ok = ok && make_map_2d(&st->Xchunk_k, e.Xchunk, e.chunk_rows, e.PT, e.PT, INFER_TILE);
     ok = ok && make_map_2d(&st->Hchunk_k, e.Hchunk, e.chunk_rows, SH, SH, INFER_TILE);
     float* w1[3] = {e.W1, e.mW1, e.vW1};
@@ -553,7 +595,9 @@ bool tc_init(Engine& e) {
     const int aux_floats = e.Bp * TILE_M;
     st->fwd1_train = pick_cfg(e.Bp, 0, st->x3);
     st->fwd2_train = pick_cfg(e.Bp, st->x3 ? 0 : aux_floats, st->x3);
-    st->bwd_train = pick_cfg(e.Bp, aux_floats, false);
+    st->x3_bwd = st->x3;
+    if (const char* v = getenv("DEEPIMPUTE_B200_EXPERIMENT")) st->simt_adam = atoi(v) & 2;
+    st->bwd_train = pick_cfg(e.Bp, aux_floats, st->x3_bwd);
     st->infer = pick_cfg(INFER_TILE, 0, st->x3);
     const int nkb = e.Bp / BLOCK_K;
     st->smem_adam = nkb * (int)(A_STAGE_BYTES + ADAM_TILE * BLOCK_K * 4) + AD_STAGES * 3 * AD_R * TILE_M * 4 + 1024;
@@ -569,7 +613,9 @@ bool tc_init(Engine& e) {
     set((const void*)tc_kernel<TC_FWD1, false>, m1); set((const void*)tc_kernel<TC_FWD1, true>, m1);
     set((const void*)tc_kernel<TC_FWD2, false>, m2); set((const void*)tc_kernel<TC_FWD2, true>, m2);
     set((const void*)tc_kernel<TC_BWD, false>, st->bwd_train.smem);
-    set((const void*)tc_adam_kernel, st->smem_adam);
+    set((const void*)tc_kernel<TC_BWD, true>, st->bwd_train.smem);
+    set((const void*)tc_adam_kernel<false>, st->smem_adam);
+    set((const void*)tc_adam_kernel<true>, st->smem_adam);
     if (ce != cudaSuccess) { e.err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return false; }
     return true;
 }
@@ -586,6 +632,7 @@ bool tc_rebind(Engine& e) {
     bool ok = true;
     ok = ok && make_map_2d(&st->Xtr_k, e.Xtr, e.n_train_pad, e.PT, e.PT, e.Bp);
     ok = ok && make_map_2d(&st->Xtr_mn, e.Xtr, e.n_train_pad, e.PT, e.PT, 32, true);
+    if (e.Xtr_lo) ok = ok && make_map_2d(&st->Xtr_lo_mn, e.Xtr_lo, e.n_train_pad, e.PT, e.PT, 32, true);
     ok = ok && make_map_plain(&st->Ytr_aux, e.Ytr, e.n_train_pad, SO, SO, st->aux_y, e.Bp);
     ok = ok && make_map_2d(&st->Xte_k, e.Xte, e.n_test_pad, e.PT, e.PT, INFER_TILE);
     st->have_split = ok;
@@ -602,6 +649,7 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
     p.n_cols = e.Bp; p.tmem_cols = pow2_cols(e.Bp);
     p.row0 = a.row0; p.rows_per_block_y = 0;
     p.Y = a.Y; p.ldy = a.ldy; p.Hact = e.Hact; p.ldh = (int64_t)e.S * e.Hp; p.DZ2 = e.DZ2; p.DZ1 = e.DZ1;
+    p.Hlo = e.Hlo; p.DZ2lo = e.DZ2lo; p.DZ1lo = e.DZ1lo;          // null unless DI_MATH_TF32X3
     p.n_valid = a.n_valid; p.training = 1; p.step = a.step;
     p.keep_scale = p.drop_thresh ? 1.0f / (1.0f - e.cfg.dropout_rate) : 1.0f;
     p.inv_norm = 1.0f / ((float)a.n_valid * (float)e.O);
@@ -619,18 +667,27 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
              launch<TC_FWD2, false>(e, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, e.S), st->fwd2_train.smem); } }
     { TcParams q = p; q.m_tiles = mh; q.row0 = 0; q.aux_cols = st->aux_h; q.aux_row0 = 0;
       q.stages = st->bwd_train.stages;
-      launch<TC_BWD, false>(e, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, e.S), st->bwd_train.smem); }
+      if (st->x3_bwd) launch<TC_BWD, true>(e, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, e.S), st->bwd_train.smem);
+      else launch<TC_BWD, false>(e, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, e.S), st->bwd_train.smem); }
+    if (st->simt_adam) { simt_adam_only(e, a); return; }
     TcParams q = p;
     q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;
+    const CUtensorMap& Xlo = which_x == 0 ? st->Xtr_lo_mn : st->Xstep_lo_mn;
     { q.which = 2; q.row0 = 0; q.wbox = st->wbox2;
       KernelTimer t(e, "adam2");
-      tc_adam_kernel<<<dim3(cdiv(e.Hp, ADAM_TILE), mo, e.S), NTHREADS, st->smem_adam, e.stream>>>(
-          st->DZ2_mn, st->H_mn, st->W2_t[0], st->W2_t[1], st->W2_t[2], q);
+      const dim3 grid(cdiv(e.Hp, ADAM_TILE), mo, e.S);
+      if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, e.stream>>>(
+          st->DZ2_mn, st->H_mn, st->DZ2lo_mn, st->Hlo_mn, st->W2_t[0], st->W2_t[1], st->W2_t[2], q);
+      else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, e.stream>>>(
+          st->DZ2_mn, st->H_mn, st->DZ2_mn, st->H_mn, st->W2_t[0], st->W2_t[1], st->W2_t[2], q);
       count_launch(e, "adam2"); }
     { q.which = 1; q.row0 = a.row0; q.wbox = st->wbox1;
       KernelTimer t(e, "adam1");
-      tc_adam_kernel<<<dim3(cdiv(e.maxPp, ADAM_TILE), mh, e.S), NTHREADS, st->smem_adam, e.stream>>>(
-          st->DZ1_mn, Xmn, st->W1_t[0], st->W1_t[1], st->W1_t[2], q);
+      const dim3 grid(cdiv(e.maxPp, ADAM_TILE), mh, e.S);
+      if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, e.stream>>>(
+          st->DZ1_mn, Xmn, st->DZ1lo_mn, Xlo, st->W1_t[0], st->W1_t[1], st->W1_t[2], q);
+      else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, e.stream>>>(
+          st->DZ1_mn, Xmn, st->DZ1_mn, Xmn, st->W1_t[0], st->W1_t[1], st->W1_t[2], q);
       count_launch(e, "adam1"); }
 }
 

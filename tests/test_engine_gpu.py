@@ -9,9 +9,11 @@ a cancelling sum):
   tf32 mode  -- tcgen05 kind::tf32: the tensor core TRUNCATES fp32 operands to 10 mantissa bits (measured: the
                 oracle in operand-truncation mode tracks it to ~2e-4 while the plain fp32 oracle differs by up to
                 8e-3), fp32 accumulate.  2e-2 of scale vs the fp32 oracle, 1e-3 vs the truncating oracle.
-  tf32x3     -- the default: forward GEMMs error-compensated (three TF32 products per fp32 product), so activations,
-                losses and predictions sit at 1e-4 of scale; the gradient GEMMs stay single-pass TF32 (2e-2 on the
-                raw gradients, which Adam's m / sqrt(v) normalisation largely cancels).
+  tf32x3     -- the default: every GEMM error-compensated (three TF32 products per fp32 product: a_hi b_hi +
+                a_hi b_lo + a_lo b_hi), so activations, losses, gradients and predictions sit at 1e-4 of scale or
+                better.  Measured end to end (test_multinet_gpu.py): single-pass TF32 gradients drift -- Adam's
+                m / sqrt(v) amplifies the relative error of small, cancelling gradient elements -- so all five
+                GEMMs are compensated, not only the forward ones.
 """
 import numpy as np
 import pytest
@@ -23,7 +25,7 @@ from oracle.multinet_oracle import OracleNet, stage
 pytestmark = pytest.mark.gpu
 
 FWD_TOL = {"fp32": 1e-5, "tf32": 2e-2, "tf32x3": 1e-4}
-MOM_TOL = {"fp32": 2e-5, "tf32": 2e-2, "tf32x3": 2e-2}
+MOM_TOL = {"fp32": 2e-5, "tf32": 2e-2, "tf32x3": 2e-4}
 LOSS_TOL = {"fp32": 5e-5, "tf32": 1e-2, "tf32x3": 1e-4}
 EPOCH_TOL = {"fp32": 5e-5, "tf32": 2e-2, "tf32x3": 1e-3}       # losses after three epochs of training
 PRED_TOL = {"fp32": 1e-4, "tf32": 3e-2, "tf32x3": 2e-3}        # predictions after three epochs of training

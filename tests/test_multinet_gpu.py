@@ -75,8 +75,10 @@ def test_fit_predict_matches_oracle_at_fixed_epochs(test_counts):
 def test_tensor_core_modes_track_the_fp32_path(test_counts):
     """The same fit on the tensor-core paths.  Measured on a B200 (5 epochs, test.csv, imputed zeros, relative to the
     fp32 path which itself sits within 1e-3 of the oracle, see above):
-      tf32   (operands truncated by the tensor core)   median 2.6e-3, 99th pct 4.5e-2, max 8.8e-2
-      tf32x3 (compensated forward GEMMs, the default)   bounds asserted below
+      tf32   (operands truncated by the tensor core)          median 2.6e-3, 99th pct 4.5e-2, max 8.8e-2
+      compensated forward GEMMs only                          median 1.1e-4, 99th pct 7.9e-3, max 2.9e-2
+      compensated forward + dz1 GEMMs                         median 2.0e-5, 99th pct 6.3e-4, max 9.0e-4
+      tf32x3 (all five GEMMs compensated, the default)        bounds asserted below
     so single-pass TF32 does NOT meet the 1e-3 target of the north star and is offered as an opt-in only."""
     from deepimpute_b200 import _lib
     if not _lib.load().di_math_mode_available(_lib.DI_MATH["tf32x3"]):
@@ -99,7 +101,7 @@ def test_tensor_core_modes_track_the_fp32_path(test_counts):
     np.testing.assert_allclose(nets["tf32x3"][0].history["loss"], nets["fp32"][0].history["loss"], rtol=1e-3)
     np.testing.assert_allclose(nets["tf32x3"][0].history["val_loss"], nets["fp32"][0].history["val_loss"], rtol=1e-3)
     assert stats["tf32"][1] < 0.1
-    assert stats["tf32x3"][1] < 1e-3 and stats["tf32x3"][0] < 2e-4
+    assert stats["tf32x3"][2] < 1e-3 and stats["tf32x3"][1] < 2e-4 and stats["tf32x3"][0] < 5e-5
     assert abs(nets["tf32x3"][0].test_metrics["correlation"] - nets["fp32"][0].test_metrics["correlation"]) < 1e-4
 
 
