@@ -504,8 +504,20 @@ int di_train_epoch(di_handle* h, const int32_t* perm, int64_t first_step, float*
     // stage this epoch's visiting order: batch i is rows [i*B, (i+1)*B) of Xtr / Ytr
     launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_pred_cols, e.PT, e.Xtr, e.B, e.Bp, e.Xtr_lo);
     launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_targ_cols, ldy, e.Ytr, e.B, e.Bp);
+    const int64_t n_steps = (e.n_train + e.B - 1) / e.B;
+    bool graphed = false;
+    if (e.cfg.math_mode != DI_MATH_FP32 && !e.profiling) {
+        // one graph launch for the whole epoch (kernels_tc.cu); the per-step Adam rates go along as a table
+        std::vector<float> lr_t((size_t)n_steps);
+        for (int64_t i = 0; i < n_steps; ++i) lr_t[(size_t)i] = adam_for_step(e, first_step + i).lr_t;
+        graphed = tc_train_epoch_graph(e, first_step, lr_t.data(), n_steps);
+        if (graphed) {
+            DI_CUDA(cudaStreamSynchronize(e.stream));       // lr_t is a stack-lifetime host buffer
+            e.adam_t = first_step + n_steps;
+        }
+    }
     int64_t step = first_step;
-    for (int64_t i0 = 0, r0 = 0; i0 < e.n_train; i0 += e.B, r0 += e.Bp, ++step) {
+    for (int64_t i0 = 0, r0 = 0; !graphed && i0 < e.n_train; i0 += e.B, r0 += e.Bp, ++step) {
         const int n_valid = (int)std::min<int64_t>(e.B, e.n_train - i0);
         int rc = run_step(e, e.Xtr, e.Ytr, r0, n_valid, step, 0);
         if (rc) return rc;

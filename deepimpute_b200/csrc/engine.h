@@ -115,6 +115,10 @@ bool tc_init(Engine& e);            // builds tensor maps; false + e.err on fail
 void tc_destroy(Engine& e);
 bool tc_rebind(Engine& e);          // after (re)allocation of X/Y buffers
 void tc_train_step(Engine& e, const StepArgs& a, int which_x);   // which_x: 0 = Xtr/Ytr, 1 = Xstep/Ystep
+// All optimiser steps of one epoch over the staged training matrices as ONE graph launch on e.stream (built on first
+// use, rebuilt when the split changes).  lr_t[i] = Adam's bias-corrected rate of step first_step + i.  Returns false
+// when the graph path is unavailable (then the caller issues the steps one by one with tc_train_step).
+bool tc_train_epoch_graph(Engine& e, int64_t first_step, const float* lr_t, int64_t n_steps);
 void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_valid, bool with_loss,
                 float* out, int64_t ld_out);                     // which_x: 2 = Xte/Yte, 3 = Xchunk
 

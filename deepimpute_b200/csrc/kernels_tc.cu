@@ -73,7 +73,21 @@ struct TcParams {
     uint32_t step; uint64_t seed; uint32_t drop_thresh; float keep_scale;
     float inv_norm;
     AdamParams adam;
+    // sub-network group of this launch: blockIdx.z counts from s_base
+    int s_base;
+    // epoch-graph mode: the launch is a node of a graph that is replayed every epoch, so what changes from epoch to
+    // epoch is read from device memory: the dropout counter is *step_base + step (step = position in the epoch)
+    // and Adam's bias-corrected rate is lr_table[step]
+    const uint32_t* step_base;
+    const float* lr_table;
 };
+
+__device__ __forceinline__ uint32_t dropout_step(const TcParams& p) { return p.step_base ? *p.step_base + p.step : p.step; }
+__device__ __forceinline__ AdamParams adam_of(const TcParams& p) {
+    AdamParams a = p.adam;
+    if (p.lr_table) a.lr_t = p.lr_table[p.step];
+    return a;
+}
 
 __device__ __forceinline__ uint32_t idesc_for(int n_cols, bool a_mn, bool b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
                                                                   const __grid_constant__ CUtensorMap mapC, const TcParams p) {
     constexpr bool A_MN = (OP != TC_BWD);
 
-    const int s = blockIdx.z;
+    const int s = blockIdx.z + p.s_base;
     const SubnetDesc d = p.desc[s];
     const int m_tile = (int)(blockIdx.y % p.m_tiles);
     const int row_tile = (int)(blockIdx.y / p.m_tiles);
@@ -238,6 +252,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
         if constexpr (OP == TC_FWD1) {
             const float bias = f_ok ? p.b1[(int64_t)s * p.Hp + f] : 0.f;
             const bool drop = p.training && p.drop_thresh;
+            const uint32_t dstep = dropout_step(p);
             float* hrow = p.Hact + row0 * p.ldh + (int64_t)s * p.Hp + f;
             float* hlo = (p.training && p.Hlo) ? p.Hlo + (int64_t)s * p.Hp + f : nullptr;   // training h starts at row 0
             for (int c = 0; c < ncol; c += 16) {
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t w[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-                    if (drop) dropout_words((uint32_t)f, (uint32_t)((c >> 2) + q), (uint32_t)d.gid, p.step, p.seed, w);
+                    if (drop) dropout_words((uint32_t)f, (uint32_t)((c >> 2) + q), (uint32_t)d.gid, dstep, p.seed, w);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float a = fmaxf(v[4 * q + i] + bias, 0.f);
@@ -295,7 +310,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
                     }
                 }
             }
-            if (p.training && f_ok) adam_update_fast(gsum, p.b2[bi], p.mb2[bi], p.vb2[bi], p.adam);
+            if (p.training && f_ok) adam_update_fast(gsum, p.b2[bi], p.mb2[bi], p.vb2[bi], adam_of(p));
             if (p.loss) {
                 double dpart = (double)part;
 #pragma unroll
@@ -326,7 +341,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
                     gsum += g;
                 }
             }
-            if (f_ok) adam_update_fast(gsum, p.b1[bi], p.mb1[bi], p.vb1[bi], p.adam);
+            if (f_ok) adam_update_fast(gsum, p.b1[bi], p.mb1[bi], p.vb1[bi], adam_of(p));
         }
     }
 
@@ -349,7 +364,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap mapW,
                                                               const __grid_constant__ CUtensorMap mapM,
                                                               const __grid_constant__ CUtensorMap mapV, const TcParams p) {
-    const int s = blockIdx.z;
+    const int s = blockIdx.z + p.s_base;
     const SubnetDesc d = p.desc[s];
     const int m0 = blockIdx.y * TILE_M;
     const int n0 = blockIdx.x * p.n_cols;
@@ -456,6 +471,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
         const int fl = warp * 32 + lane;
         const bool f_ok = (m0 + fl) < out_dim;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        const AdamParams adam = adam_of(p);
         mbar_wait(&tmem_full_bar, 0, 4);
         tc_fence_after();
         for (int c = 0; c < nchunks; ++c) {
@@ -469,7 +485,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
                 for (int r = 0; r < AD_R; ++r) {
                     const int idx = r * wbox + fl;
                     float w = ws[idx], m = ws[tile_floats + idx], v = ws[2 * tile_floats + idx];
-                    adam_update_fast(g[r], w, m, v, p.adam);
+                    adam_update_fast(g[r], w, m, v, adam);
                     ws[idx] = w; ws[tile_floats + idx] = m; ws[2 * tile_floats + idx] = v;
                 }
             }
@@ -496,13 +512,29 @@ struct TcState {
     // staged train / test matrices (rebuilt by tc_rebind)
     CUtensorMap Xtr_k, Xtr_mn, Xte_k, Ytr_aux;
     bool have_split = false;
-    struct Cfg { int stages = 0, smem = 0; };
-    Cfg fwd1_train, fwd2_train, bwd_train, infer;          // ring depth and dynamic shared memory per launch
+    struct Cfg { int stages = 0, smem = 0; bool aux = false; };
+    Cfg fwd1_train[2], fwd2_train[2], bwd_train[2], infer;   // [0]: two CTAs per SM where possible, [1]: deepest ring
+    // epoch graph over sub-network groups
+    int n_groups = 1, group_deep = 0;
+    int group_s0[9] = {0};
+    cudaStream_t gstream[8][2] = {};
+    cudaEvent_t gev[8][3] = {};
+    cudaEvent_t ev_fork = nullptr;
+    cudaGraphExec_t epoch_exec = nullptr;
+    int64_t graph_nodes = 0, graph_n_train = -1, lr_capacity = 0;
+    uint32_t* d_step_base = nullptr;
+    float* d_lr_table = nullptr;
+    bool use_graph = true, graph_failed = false;
     int smem_adam = 0;
     bool x3 = false;                                       // forward GEMMs error-compensated (DI_MATH_TF32X3)
     bool x3_bwd = false, simt_adam = false;                // experiments (DEEPIMPUTE_B200_EXPERIMENT bit 0 / bit 1)
     int aux_h = 0, aux_y = 0, wbox1 = 0, wbox2 = 0;
 };
+
+void drop_epoch_graph(TcState* st) {
+    if (st->epoch_exec) { cudaGraphExecDestroy(st->epoch_exec); st->epoch_exec = nullptr; }
+    st->graph_nodes = 0;
+}
 
 int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 int smem_for(int n_cols, int stages, int aux_floats, bool x3) {
@@ -510,9 +542,11 @@ int smem_for(int n_cols, int stages, int aux_floats, bool x3) {
 }
 // deepest ring (<= MAX_STAGES) that still leaves room for two CTAs per SM; if even two stages do not fit in half an
 // SM, the deepest ring that fits in one
-TcState::Cfg pick_cfg(int n_cols, int aux_floats, bool x3) {
+TcState::Cfg pick_cfg(int n_cols, int aux_floats, bool x3, bool deep = false) {
     TcState::Cfg c;
+    c.aux = aux_floats > 0;
     for (int budget : {110 * 1024, 224 * 1024}) {
+        if (deep && budget < 200 * 1024) continue;
         for (int s = MAX_STAGES; s >= 2; --s)
             if (smem_for(n_cols, s, aux_floats, x3) <= budget) { c.stages = s; c.smem = smem_for(n_cols, s, aux_floats, x3); return c; }
     }
@@ -593,27 +627,50 @@ bool tc_init(Engine& e) {
     // would otherwise push it to one CTA per SM (its 4 x S CTAs are more than one CTA per SM can hold in one wave).
     st->x3 = e.cfg.math_mode == DI_MATH_TF32X3;
     const int aux_floats = e.Bp * TILE_M;
-    st->fwd1_train = pick_cfg(e.Bp, 0, st->x3);
-    st->fwd2_train = pick_cfg(e.Bp, st->x3 ? 0 : aux_floats, st->x3);
     st->x3_bwd = st->x3;
     if (const char* v = getenv("DEEPIMPUTE_B200_EXPERIMENT")) st->simt_adam = atoi(v) & 2;
-    st->bwd_train = pick_cfg(e.Bp, aux_floats, st->x3_bwd);
+    for (int deep = 0; deep < 2; ++deep) {
+        st->fwd1_train[deep] = pick_cfg(e.Bp, 0, st->x3, deep);
+        st->fwd2_train[deep] = pick_cfg(e.Bp, (st->x3 && !deep) ? 0 : aux_floats, st->x3, deep);
+        st->bwd_train[deep] = pick_cfg(e.Bp, aux_floats, st->x3, deep);
+    }
     st->infer = pick_cfg(INFER_TILE, 0, st->x3);
+    // sub-network groups of the epoch graph: independent chains on their own streams
+    int G = std::min(4, e.S);
+    if (const char* v = getenv("DEEPIMPUTE_B200_GROUPS")) G = std::max(1, std::min(std::min(8, e.S), atoi(v)));
+    if (const char* v = getenv("DEEPIMPUTE_B200_GRAPH")) st->use_graph = atoi(v) != 0;
+    st->n_groups = G;
+    for (int g = 0; g <= G; ++g) st->group_s0[g] = (int)((int64_t)e.S * g / G);
+    // a group's forward / backward grids are small: when all of them fit one CTA per SM, use the deep rings
+    const int per_group = (e.S + G - 1) / G;
+    st->group_deep = (per_group * cdiv(e.Op, TILE_M) <= 148) ? 1 : 0;
+    if (const char* v = getenv("DEEPIMPUTE_B200_DEEP")) st->group_deep = atoi(v) != 0;
+    for (int g = 0; g < G; ++g) {
+        for (int k = 0; k < 2; ++k)
+            if (cudaStreamCreateWithFlags(&st->gstream[g][k], cudaStreamNonBlocking) != cudaSuccess) { e.err = "cudaStreamCreate failed"; return false; }
+        for (int k = 0; k < 3; ++k)
+            if (cudaEventCreateWithFlags(&st->gev[g][k], cudaEventDisableTiming) != cudaSuccess) { e.err = "cudaEventCreate failed"; return false; }
+    }
+    if (cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMalloc((void**)&st->d_step_base, sizeof(uint32_t)) != cudaSuccess) { e.err = "epoch-graph set-up failed"; return false; }
     const int nkb = e.Bp / BLOCK_K;
     st->smem_adam = nkb * (int)(A_STAGE_BYTES + ADAM_TILE * BLOCK_K * 4) + AD_STAGES * 3 * AD_R * TILE_M * 4 + 1024;
-    if (st->smem_adam > 227 * 1024 || !st->fwd1_train.stages || !st->fwd2_train.stages || !st->bwd_train.stages || !st->infer.stages) {
+    if (st->smem_adam > 227 * 1024 || !st->fwd1_train[0].stages || !st->fwd2_train[0].stages || !st->bwd_train[0].stages ||
+        !st->fwd1_train[1].stages || !st->fwd2_train[1].stages || !st->bwd_train[1].stages || !st->infer.stages) {
         e.err = "tensor-core math modes: this batch size needs more shared memory than one SM has (use math mode fp32)";
         return false;
     }
-    const int m1 = std::max(st->fwd1_train.smem, st->infer.smem), m2 = std::max(st->fwd2_train.smem, st->infer.smem);
+    const int m1 = std::max(std::max(st->fwd1_train[0].smem, st->fwd1_train[1].smem), st->infer.smem);
+    const int m2 = std::max(std::max(st->fwd2_train[0].smem, st->fwd2_train[1].smem), st->infer.smem);
+    const int m3 = std::max(st->bwd_train[0].smem, st->bwd_train[1].smem);
     cudaError_t ce = cudaSuccess;
     auto set = [&](const void* fn, int bytes) {
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     };
     set((const void*)tc_kernel<TC_FWD1, false>, m1); set((const void*)tc_kernel<TC_FWD1, true>, m1);
     set((const void*)tc_kernel<TC_FWD2, false>, m2); set((const void*)tc_kernel<TC_FWD2, true>, m2);
-    set((const void*)tc_kernel<TC_BWD, false>, st->bwd_train.smem);
-    set((const void*)tc_kernel<TC_BWD, true>, st->bwd_train.smem);
+    set((const void*)tc_kernel<TC_BWD, false>, m3);
+    set((const void*)tc_kernel<TC_BWD, true>, m3);
     set((const void*)tc_adam_kernel<false>, st->smem_adam);
     set((const void*)tc_adam_kernel<true>, st->smem_adam);
     if (ce != cudaSuccess) { e.err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return false; }
@@ -621,7 +678,18 @@ bool tc_init(Engine& e) {
 }
 
 void tc_destroy(Engine& e) {
-    delete static_cast<TcState*>(e.tc);
+    auto* st = static_cast<TcState*>(e.tc);
+    if (st) {
+        drop_epoch_graph(st);
+        for (int g = 0; g < 8; ++g) {
+            for (int k = 0; k < 2; ++k) if (st->gstream[g][k]) cudaStreamDestroy(st->gstream[g][k]);
+            for (int k = 0; k < 3; ++k) if (st->gev[g][k]) cudaEventDestroy(st->gev[g][k]);
+        }
+        if (st->ev_fork) cudaEventDestroy(st->ev_fork);
+        if (st->d_step_base) cudaFree(st->d_step_base);
+        if (st->d_lr_table) cudaFree(st->d_lr_table);
+    }
+    delete st;
     e.tc = nullptr;
 }
 
@@ -636,12 +704,34 @@ bool tc_rebind(Engine& e) {
     ok = ok && make_map_plain(&st->Ytr_aux, e.Ytr, e.n_train_pad, SO, SO, st->aux_y, e.Bp);
     ok = ok && make_map_2d(&st->Xte_k, e.Xte, e.n_test_pad, e.PT, e.PT, INFER_TILE);
     st->have_split = ok;
+    drop_epoch_graph(st);             // the graph's nodes hold the old tensor maps
+    st->graph_failed = false;
     if (!ok) e.err = "cuTensorMapEncodeTiled failed (staged matrices)";
     return ok;
 }
 
-void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
-    auto* st = static_cast<TcState*>(e.tc);
+namespace {
+
+// Where and how one optimiser step of one sub-network group is launched.
+struct StepPlan {
+    int s0 = 0, ns = 0;                         // sub-networks [s0, s0 + ns)
+    cudaStream_t main = nullptr, side = nullptr; // side != nullptr: ADAM2 runs there, beside ADAM1
+    cudaEvent_t ev_bwd = nullptr, ev_adam2 = nullptr;
+    bool graph = false;                          // node of the epoch graph: per-epoch values come from device tables
+    bool first = false;                          // first step of the capture (nothing to wait for)
+    int deep = 0;                                // 1: deep-ring configs (one CTA per SM), for small grids
+};
+
+template <int OP, bool X3>
+void launch_on(Engine& e, const StepPlan& pl, const char* name, const CUtensorMap& a, const CUtensorMap& b,
+               const CUtensorMap& c, const TcParams& p, dim3 grid, int smem) {
+    if (pl.graph) { tc_kernel<OP, X3><<<grid, NTHREADS, smem, pl.main>>>(a, b, c, p); return; }
+    KernelTimer t(e, name);
+    tc_kernel<OP, X3><<<grid, NTHREADS, smem, pl.main>>>(a, b, c, p);
+    count_launch(e, name);
+}
+
+void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const StepPlan& pl) {
     const CUtensorMap& Xk = which_x == 0 ? st->Xtr_k : st->Xstep_k;
     const CUtensorMap& Xmn = which_x == 0 ? st->Xtr_mn : st->Xstep_mn;
     const CUtensorMap& Yaux = which_x == 0 ? st->Ytr_aux : st->Ystep_aux;
@@ -654,41 +744,128 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
     p.keep_scale = p.drop_thresh ? 1.0f / (1.0f - e.cfg.dropout_rate) : 1.0f;
     p.inv_norm = 1.0f / ((float)a.n_valid * (float)e.O);
     p.loss = e.d_loss; p.adam = a.adam;
+    p.s_base = pl.s0;
+    if (pl.graph) { p.step_base = st->d_step_base; p.lr_table = st->d_lr_table; }
     const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
+    const TcState::Cfg& c1 = st->fwd1_train[pl.deep];
+    const TcState::Cfg& c2 = st->fwd2_train[pl.deep];
+    const TcState::Cfg& c3 = st->bwd_train[pl.deep];
 
+    // the previous step's ADAM2 (side stream) still reads h and dz2, which FWD1 / FWD2 are about to overwrite, and
+    // writes W2, which FWD2 reads: the new step starts when it is done (ADAM2 therefore overlaps ADAM1 only)
+    if (pl.side && !pl.first) cudaStreamWaitEvent(pl.main, pl.ev_adam2, 0);
     { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
-      q.stages = st->fwd1_train.stages;
-      if (st->x3) launch<TC_FWD1, true>(e, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, e.S), st->fwd1_train.smem);
-      else launch<TC_FWD1, false>(e, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, e.S), st->fwd1_train.smem); }
+      q.stages = c1.stages;
+      if (st->x3) launch_on<TC_FWD1, true>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem);
+      else launch_on<TC_FWD1, false>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem); }
     { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
-      q.stages = st->fwd2_train.stages;
-      if (st->x3) launch<TC_FWD2, true>(e, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, e.S), st->fwd2_train.smem);
-      else { q.aux_cols = st->aux_y; q.aux_row0 = a.row0;
-             launch<TC_FWD2, false>(e, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, e.S), st->fwd2_train.smem); } }
+      q.stages = c2.stages;
+      if (c2.aux) { q.aux_cols = st->aux_y; q.aux_row0 = a.row0; }
+      if (st->x3) launch_on<TC_FWD2, true>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem);
+      else launch_on<TC_FWD2, false>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem); }
     { TcParams q = p; q.m_tiles = mh; q.row0 = 0; q.aux_cols = st->aux_h; q.aux_row0 = 0;
-      q.stages = st->bwd_train.stages;
-      if (st->x3_bwd) launch<TC_BWD, true>(e, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, e.S), st->bwd_train.smem);
-      else launch<TC_BWD, false>(e, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, e.S), st->bwd_train.smem); }
-    if (st->simt_adam) { simt_adam_only(e, a); return; }
+      q.stages = c3.stages;
+      if (st->x3) launch_on<TC_BWD, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem);
+      else launch_on<TC_BWD, false>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem); }
+    if (st->simt_adam && !pl.graph) { simt_adam_only(e, a); return; }
     TcParams q = p;
     q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;
     const CUtensorMap& Xlo = which_x == 0 ? st->Xtr_lo_mn : st->Xstep_lo_mn;
+    cudaStream_t s2 = pl.side ? pl.side : pl.main;
+    if (pl.side) { cudaEventRecord(pl.ev_bwd, pl.main); cudaStreamWaitEvent(pl.side, pl.ev_bwd, 0); }
     { q.which = 2; q.row0 = 0; q.wbox = st->wbox2;
-      KernelTimer t(e, "adam2");
-      const dim3 grid(cdiv(e.Hp, ADAM_TILE), mo, e.S);
-      if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, e.stream>>>(
+      const dim3 grid(cdiv(e.Hp, ADAM_TILE), mo, pl.ns);
+      KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam2");
+      if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, s2>>>(
           st->DZ2_mn, st->H_mn, st->DZ2lo_mn, st->Hlo_mn, st->W2_t[0], st->W2_t[1], st->W2_t[2], q);
-      else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, e.stream>>>(
+      else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, s2>>>(
           st->DZ2_mn, st->H_mn, st->DZ2_mn, st->H_mn, st->W2_t[0], st->W2_t[1], st->W2_t[2], q);
-      count_launch(e, "adam2"); }
+      if (t) { delete t; count_launch(e, "adam2"); } }
+    if (pl.side) cudaEventRecord(pl.ev_adam2, pl.side);
     { q.which = 1; q.row0 = a.row0; q.wbox = st->wbox1;
-      KernelTimer t(e, "adam1");
-      const dim3 grid(cdiv(e.maxPp, ADAM_TILE), mh, e.S);
-      if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, e.stream>>>(
+      int maxPp = 0;
+      for (int s = pl.s0; s < pl.s0 + pl.ns; ++s) maxPp = std::max(maxPp, e.Pp[s]);
+      const dim3 grid(cdiv(maxPp, ADAM_TILE), mh, pl.ns);
+      KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam1");
+      if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, pl.main>>>(
           st->DZ1_mn, Xmn, st->DZ1lo_mn, Xlo, st->W1_t[0], st->W1_t[1], st->W1_t[2], q);
-      else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, e.stream>>>(
+      else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, pl.main>>>(
           st->DZ1_mn, Xmn, st->DZ1_mn, Xmn, st->W1_t[0], st->W1_t[1], st->W1_t[2], q);
-      count_launch(e, "adam1"); }
+      if (t) { delete t; count_launch(e, "adam1"); } }
+}
+
+// Capture one whole epoch -- every optimiser step of every sub-network group -- into a graph that is replayed with a
+// single launch per epoch.  Sub-network groups are independent models (reference multinet.py:132-148: the branches
+// share nothing), so each group's chain FWD1 -> FWD2 -> BWD -> {ADAM1 | ADAM2} runs on its own pair of streams and
+// the latency-bound kernels of one group overlap the bandwidth-bound ones of another.
+bool build_epoch_graph(Engine& e, TcState* st) {
+    drop_epoch_graph(st);
+    const int64_t n_steps = (e.n_train + e.B - 1) / e.B;
+    if (n_steps <= 0) return false;
+    if (st->lr_capacity < n_steps) {
+        if (st->d_lr_table) cudaFree(st->d_lr_table);
+        st->d_lr_table = nullptr; st->lr_capacity = 0;
+        if (cudaMalloc((void**)&st->d_lr_table, (size_t)n_steps * sizeof(float)) != cudaSuccess) return false;
+        st->lr_capacity = n_steps;
+    }
+    const int G = st->n_groups;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(e.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    cudaMemsetAsync(e.d_loss, 0, sizeof(double), e.stream);
+    cudaEventRecord(st->ev_fork, e.stream);
+    for (int g = 0; g < G; ++g) cudaStreamWaitEvent(st->gstream[g][0], st->ev_fork, 0);
+    const int64_t ldy = (int64_t)e.S * e.Op;
+    for (int64_t i = 0; i < n_steps; ++i) {
+        StepArgs a;
+        a.X = e.Xtr; a.Y = e.Ytr; a.ldx = e.PT; a.ldy = ldy; a.row0 = i * e.Bp;
+        a.n_valid = (int)std::min<int64_t>(e.B, e.n_train - i * e.B);
+        a.step = (uint32_t)i;                      // position in the epoch; the kernels add *d_step_base
+        a.adam = AdamParams{0.f, 1.0f - e.cfg.beta1, 1.0f - e.cfg.beta2, e.cfg.epsilon};   // lr_t comes from d_lr_table
+        for (int g = 0; g < G; ++g) {
+            StepPlan pl;
+            pl.s0 = st->group_s0[g]; pl.ns = st->group_s0[g + 1] - st->group_s0[g];
+            pl.main = st->gstream[g][0]; pl.side = st->gstream[g][1];
+            pl.ev_bwd = st->gev[g][0]; pl.ev_adam2 = st->gev[g][1];
+            pl.graph = true; pl.first = (i == 0); pl.deep = st->group_deep;
+            launch_step(e, st, a, 0, pl);
+        }
+    }
+    for (int g = 0; g < G; ++g) {
+        cudaStreamWaitEvent(st->gstream[g][0], st->gev[g][1], 0);      // join the side stream
+        cudaEventRecord(st->gev[g][2], st->gstream[g][0]);
+        cudaStreamWaitEvent(e.stream, st->gev[g][2], 0);
+    }
+    cudaError_t ce = cudaStreamEndCapture(e.stream, &graph);
+    if (ce != cudaSuccess || !graph) { cudaGetLastError(); return false; }
+    ce = cudaGraphInstantiate(&st->epoch_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { cudaGetLastError(); st->epoch_exec = nullptr; return false; }
+    st->graph_nodes = n_steps * G * 5;
+    st->graph_n_train = e.n_train;
+    return true;
+}
+
+}  // namespace
+
+void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
+    auto* st = static_cast<TcState*>(e.tc);
+    StepPlan pl;
+    pl.s0 = 0; pl.ns = e.S; pl.main = e.stream;
+    launch_step(e, st, a, which_x, pl);
+}
+
+bool tc_train_epoch_graph(Engine& e, int64_t first_step, const float* lr_t, int64_t n_steps) {
+    auto* st = static_cast<TcState*>(e.tc);
+    if (!st || !st->use_graph || st->simt_adam) return false;
+    if (!st->epoch_exec || st->graph_n_train != e.n_train) {
+        if (st->graph_failed || !build_epoch_graph(e, st)) { st->graph_failed = true; return false; }
+    }
+    const uint32_t base = (uint32_t)first_step;
+    if (cudaMemcpyAsync(st->d_step_base, &base, sizeof base, cudaMemcpyHostToDevice, e.stream) != cudaSuccess) return false;
+    if (cudaMemcpyAsync(st->d_lr_table, lr_t, (size_t)n_steps * sizeof(float), cudaMemcpyHostToDevice, e.stream) != cudaSuccess) return false;
+    if (cudaGraphLaunch(st->epoch_exec, e.stream) != cudaSuccess) { cudaGetLastError(); return false; }
+    e.launches += st->graph_nodes;
+    return true;
 }
 
 void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_valid, bool with_loss,

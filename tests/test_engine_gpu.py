@@ -25,7 +25,7 @@ from oracle.multinet_oracle import OracleNet, stage
 pytestmark = pytest.mark.gpu
 
 FWD_TOL = {"fp32": 1e-5, "tf32": 2e-2, "tf32x3": 1e-4}
-MOM_TOL = {"fp32": 2e-5, "tf32": 2e-2, "tf32x3": 2e-4}
+MOM_TOL = {"fp32": 2e-5, "tf32": 1e-1, "tf32x3": 2e-4}     # tf32: relu-mask flips leak into dW1/db1
 LOSS_TOL = {"fp32": 5e-5, "tf32": 1e-2, "tf32x3": 1e-4}
 EPOCH_TOL = {"fp32": 5e-5, "tf32": 2e-2, "tf32x3": 1e-3}       # losses after three epochs of training
 PRED_TOL = {"fp32": 1e-4, "tf32": 3e-2, "tf32x3": 2e-3}        # predictions after three epochs of training
