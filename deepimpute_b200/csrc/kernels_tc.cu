@@ -38,20 +38,22 @@ enum { TC_FWD1 = 0, TC_FWD2 = 1, TC_BWD = 2 };
 
 constexpr int TILE_M = 128;              // TMEM lanes = output features per CTA
 constexpr int NTHREADS = 192;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr uint32_t A_STAGE_BYTES = TILE_M * BLOCK_K * 4;       // 16 KB
 
 constexpr int INFER_TILE = 128;      // cells per CTA at inference (UMMA N)
 constexpr int ADAM_TILE = 128;       // input features per CTA in the weight-gradient kernel (UMMA N)
 constexpr int AD_R = 8;              // weight rows per streamed chunk
-constexpr int AD_STAGES = 3;         // chunks of w/m/v in the shared-memory ring
+constexpr int AD_STAGES = 3;         // chunks of w/m/v in the dedicated part of the shared-memory ring
+constexpr int AD_MAX_RING = 12;      // ... plus the stages that reuse the operand buffers once the MMAs are done
 
 struct TcParams {
     const SubnetDesc* desc;
     int S, H, O, Hp, Op;
     int n_cols;                 // UMMA N: batch rows (FWD*/BWD) or input-feature tile width (ADAM)
     int tmem_cols;              // power of two >= n_cols
-    int stages;
+    int stages;                 // ring of raw (hi) slabs written by TMA
+    int lo_stages;              // X3: ring of residual (lo) slabs written by the converter warps
     int which;                  // ADAM: 1 = W1 (in = X, dout = dz1), 2 = W2 (in = h, dout = dz2)
     int nkb_adam;               // ADAM: K blocks = padded batch rows / 32
     int64_t row0;               // first row of the batch / cell tile group inside the B-operand tensor
@@ -149,18 +151,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t b_stage_bytes = (uint32_t)p.n_cols * BLOCK_K * 4;
-    const uint32_t hi_bytes = A_STAGE_BYTES + b_stage_bytes;           // what TMA writes per stage
-    const uint32_t stage_bytes = X3 ? 2 * hi_bytes : hi_bytes;         // X3: [A_hi | B_hi | A_lo | B_lo]
+    const uint32_t hi_bytes = A_STAGE_BYTES + b_stage_bytes;           // one slab: [A | B], what TMA writes per K block
+    const uint32_t stage_bytes = hi_bytes;
     const int stages = p.stages;
-    const float* aux = reinterpret_cast<const float*>(smem + (size_t)stages * stage_bytes);
-    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], conv_bar[MAX_STAGES], tmem_full_bar, aux_bar;
+    const int lo_stages = X3 ? p.lo_stages : 0;
+    // shared memory: [raw ring: stages slabs][X3: residual ring: lo_stages slabs][aux tile]
+    uint8_t* lo_base = smem + (size_t)stages * stage_bytes;
+    const float* aux = reinterpret_cast<const float*>(lo_base + (size_t)lo_stages * stage_bytes);
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], lo_ready[MAX_STAGES], lo_free[MAX_STAGES], tmem_full_bar, aux_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ double red[4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&conv_bar[i], 128); }
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < lo_stages; ++i) { mbar_init(&lo_ready[i], 128); mbar_init(&lo_free[i], 1); }
         mbar_init(&tmem_full_bar, 1);
         mbar_init(&aux_bar, 1);
         fence_barrier_init();
@@ -196,12 +202,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
             const uint32_t idesc = idesc_for(p.n_cols, A_MN, false);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % stages;
-                mbar_wait(X3 ? &conv_bar[st] : &full_bar[st], (kb / stages) & 1, 3);
+                mbar_wait(&full_bar[st], (kb / stages) & 1, 3);
+                const int ls = X3 ? kb % lo_stages : 0;
+                if constexpr (X3) mbar_wait(&lo_ready[ls], (kb / lo_stages) & 1, 10);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                 const uint32_t sb = sa + A_STAGE_BYTES;
                 if constexpr (X3) {
-                    const uint32_t sa_lo = sa + hi_bytes, sb_lo = sb + hi_bytes;
+                    const uint32_t sa_lo = smem_u32(lo_base + (size_t)ls * stage_bytes), sb_lo = sa_lo + A_STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
                         umma_tf32(tmem, stage_desc<A_MN>(sa_lo, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
@@ -214,6 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
                         umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[st]);
+                if constexpr (X3) umma_commit(&lo_free[ls]);
             }
             umma_commit(&tmem_full_bar);
         }
@@ -225,24 +234,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
         const int ncol = p.n_cols;
         if constexpr (X3) {
-            // residual pass: lo = a - trunc19(a) for every float of the slab TMA just delivered
-            const int nvec = (int)(hi_bytes / 16);
+            // residual pass: lo = a - trunc19(a) for every float of the slab TMA just delivered, written to the next
+            // slab of the residual ring (element-wise: the swizzled layout carries over unchanged)
+            const int per_thread = (int)(hi_bytes / 16) / 128;          // float4 per thread; hi_bytes is a multiple of 4 KB
             for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % stages;
+                const int st = kb % stages, ls = kb % lo_stages;
                 mbar_wait(&full_bar[st], (kb / stages) & 1, 1);
-                const float4* hi = reinterpret_cast<const float4*>(smem + (size_t)st * stage_bytes);
-                float4* lo = reinterpret_cast<float4*>(smem + (size_t)st * stage_bytes + hi_bytes);
-                for (int i = threadIdx.x; i < nvec; i += 128) {
-                    const float4 v = hi[i];
-                    float4 r;
-                    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                    lo[i] = r;
+                if (kb >= lo_stages) mbar_wait(&lo_free[ls], ((kb / lo_stages) - 1) & 1, 11);
+                const uint32_t hi = smem_u32(smem + (size_t)st * stage_bytes) + threadIdx.x * 16;
+                const uint32_t lo = smem_u32(lo_base + (size_t)ls * stage_bytes) + threadIdx.x * 16;
+                for (int i0 = 0; i0 < per_thread; i0 += 4) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + u < per_thread)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                         : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(hi + (i0 + u) * 2048));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + u < per_thread)
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
+                                         ::"r"(lo + (i0 + u) * 2048), "f"(tf32_residual(v[u].x)), "f"(tf32_residual(v[u].y)),
+                                           "f"(tf32_residual(v[u].z)), "f"(tf32_residual(v[u].w)) : "memory");
                 }
                 fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core
-                mbar_arrive(&conv_bar[st]);
+                mbar_arrive(&lo_ready[ls]);
             }
         }
         if (p.aux_cols > 0) mbar_wait(&aux_bar, 0, 5);
@@ -386,13 +402,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     const int wbox = p.wbox;
     const int tile_floats = AD_R * wbox;                  // one tensor, one chunk
     const uint32_t chunk_bytes = 3u * tile_floats * 4u;
-    __shared__ uint64_t ops_bar, mma_bar, tmem_full_bar, wfull[AD_STAGES], wdone[AD_STAGES];
+    // ring stages: AD_STAGES dedicated ones, then as many as fit in the operand buffers, which are dead once the
+    // accumulator is complete -- the deeper ring is what keeps enough bytes in flight to cover HBM latency
+    const uint32_t ops_bytes = (uint32_t)nkb * (A_STAGE_BYTES + b_block_bytes);
+    const int ring = min(AD_MAX_RING, AD_STAGES + (int)(ops_bytes / chunk_bytes));
+    auto stage_ptr = [&](int st) -> float* {
+        return st < AD_STAGES ? wring + (size_t)st * 3 * tile_floats
+                              : reinterpret_cast<float*>(smem + (size_t)(st - AD_STAGES) * chunk_bytes);
+    };
+    __shared__ uint64_t ops_bar, mma_bar, tmem_full_bar, wfull[AD_MAX_RING], wdone[AD_MAX_RING];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(&ops_bar, 1); mbar_init(&mma_bar, 1); mbar_init(&tmem_full_bar, 1);
-        for (int i = 0; i < AD_STAGES; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wdone[i], 128); }
+        for (int i = 0; i < ring; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wdone[i], 128); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
@@ -402,8 +426,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     const uint32_t tmem = tmem_base_slot;
 
     auto load_chunk = [&](int c) {                        // one elected thread
-        const int st = c % AD_STAGES;
-        float* ws = wring + (size_t)st * 3 * tile_floats;
+        const int st = c % ring;
+        float* ws = stage_ptr(st);
         const int32_t r = (int32_t)(row_base + n0 + c * AD_R);
         mbar_arrive_expect_tx(&wfull[st], chunk_bytes);
         tma_load_2d(ws, &mapW, &wfull[st], m0, r);
@@ -433,18 +457,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
                 mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * (A_STAGE_BYTES + b_block_bytes));
                 load_a(&mapAlo); load_b(&mapB);                    // round 2: dout_lo, in_hi
             }
+            if (ring > AD_STAGES) {                                // the operand buffers join the ring
+                mbar_wait(&tmem_full_bar, 0, 4);
+                for (int c = AD_STAGES; c < min(ring, nchunks); ++c) load_chunk(c);
+            }
             for (int c = 0; c < nchunks; ++c) {
-                const int st = c % AD_STAGES;
-                float* ws = wring + (size_t)st * 3 * tile_floats;
-                mbar_wait(&wdone[st], (c / AD_STAGES) & 1, 8);      // all 128 epilogue threads updated this chunk
+                const int st = c % ring;
+                float* ws = stage_ptr(st);
+                mbar_wait(&wdone[st], (c / ring) & 1, 8);           // all 128 epilogue threads updated this chunk
                 const int32_t r = (int32_t)(row_base + n0 + c * AD_R);
                 tma_store_2d(&mapW, ws, m0, r);
                 tma_store_2d(&mapM, ws + tile_floats, m0, r);
                 tma_store_2d(&mapV, ws + 2 * tile_floats, m0, r);
                 bulk_commit();
-                if (c + AD_STAGES < nchunks) {
+                if (c + ring < nchunks) {
                     bulk_wait_read<0>();                         // the stores have read the stage: refill it
-                    load_chunk(c + AD_STAGES);
+                    load_chunk(c + ring);
                 }
             }
             bulk_wait<0>();
@@ -475,11 +503,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
         mbar_wait(&tmem_full_bar, 0, 4);
         tc_fence_after();
         for (int c = 0; c < nchunks; ++c) {
-            const int st = c % AD_STAGES;
-            float* ws = wring + (size_t)st * 3 * tile_floats;
+            const int st = c % ring;
+            float* ws = stage_ptr(st);
             float g[AD_R];
             tmem_ld8(taddr + c * AD_R, g);
-            mbar_wait(&wfull[st], (c / AD_STAGES) & 1, 7);
+            mbar_wait(&wfull[st], (c / ring) & 1, 7);
             if (f_ok) {
 #pragma unroll
                 for (int r = 0; r < AD_R; ++r) {
@@ -512,7 +540,7 @@ struct TcState {
     // staged train / test matrices (rebuilt by tc_rebind)
     CUtensorMap Xtr_k, Xtr_mn, Xte_k, Ytr_aux;
     bool have_split = false;
-    struct Cfg { int stages = 0, smem = 0; bool aux = false; };
+    struct Cfg { int stages = 0, lo_stages = 0, smem = 0; bool aux = false; };
     Cfg fwd1_train[2], fwd2_train[2], bwd_train[2], infer;   // [0]: two CTAs per SM where possible, [1]: deepest ring
     // epoch graph over sub-network groups
     int n_groups = 1, group_deep = 0;
@@ -537,18 +565,24 @@ void drop_epoch_graph(TcState* st) {
 }
 
 int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
-int smem_for(int n_cols, int stages, int aux_floats, bool x3) {
-    return stages * (x3 ? 2 : 1) * (int)(A_STAGE_BYTES + n_cols * BLOCK_K * 4) + aux_floats * 4 + 1024;
+int smem_for(int n_cols, int stages, int lo_stages, int aux_floats) {
+    return (stages + lo_stages) * (int)(A_STAGE_BYTES + n_cols * BLOCK_K * 4) + aux_floats * 4 + 1024;
 }
 // deepest ring (<= MAX_STAGES) that still leaves room for two CTAs per SM; if even two stages do not fit in half an
 // SM, the deepest ring that fits in one
 TcState::Cfg pick_cfg(int n_cols, int aux_floats, bool x3, bool deep = false) {
+    // (raw slabs, residual slabs) in order of preference; the first that fits the budget wins
+    static const int plain[][2] = {{6, 0}, {5, 0}, {4, 0}, {3, 0}, {2, 0}};
+    static const int comp[][2] = {{5, 3}, {4, 3}, {4, 2}, {3, 2}, {2, 2}, {2, 1}};
     TcState::Cfg c;
     c.aux = aux_floats > 0;
     for (int budget : {110 * 1024, 224 * 1024}) {
         if (deep && budget < 200 * 1024) continue;
-        for (int s = MAX_STAGES; s >= 2; --s)
-            if (smem_for(n_cols, s, aux_floats, x3) <= budget) { c.stages = s; c.smem = smem_for(n_cols, s, aux_floats, x3); return c; }
+        for (int i = 0; i < (x3 ? 6 : 5); ++i) {
+            const int hs = x3 ? comp[i][0] : plain[i][0], ls = x3 ? comp[i][1] : 0;
+            const int bytes = smem_for(n_cols, hs, ls, aux_floats);
+            if (bytes <= budget) { c.stages = hs; c.lo_stages = ls; c.smem = bytes; return c; }
+        }
     }
     return c;      // stages == 0: does not fit
 }
@@ -634,7 +668,7 @@ bool tc_init(Engine& e) {
         st->fwd2_train[deep] = pick_cfg(e.Bp, (st->x3 && !deep) ? 0 : aux_floats, st->x3, deep);
         st->bwd_train[deep] = pick_cfg(e.Bp, aux_floats, st->x3, deep);
     }
-    st->infer = pick_cfg(INFER_TILE, 0, st->x3);
+    st->infer = pick_cfg(INFER_TILE, 0, st->x3, true);
     // sub-network groups of the epoch graph: independent chains on their own streams
     int G = std::min(4, e.S);
     if (const char* v = getenv("DEEPIMPUTE_B200_GROUPS")) G = std::max(1, std::min(std::min(8, e.S), atoi(v)));
@@ -755,16 +789,16 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     // writes W2, which FWD2 reads: the new step starts when it is done (ADAM2 therefore overlaps ADAM1 only)
     if (pl.side && !pl.first) cudaStreamWaitEvent(pl.main, pl.ev_adam2, 0);
     { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
-      q.stages = c1.stages;
+      q.stages = c1.stages; q.lo_stages = c1.lo_stages;
       if (st->x3) launch_on<TC_FWD1, true>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem);
       else launch_on<TC_FWD1, false>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem); }
     { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
-      q.stages = c2.stages;
+      q.stages = c2.stages; q.lo_stages = c2.lo_stages;
       if (c2.aux) { q.aux_cols = st->aux_y; q.aux_row0 = a.row0; }
       if (st->x3) launch_on<TC_FWD2, true>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem);
       else launch_on<TC_FWD2, false>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem); }
     { TcParams q = p; q.m_tiles = mh; q.row0 = 0; q.aux_cols = st->aux_h; q.aux_row0 = 0;
-      q.stages = c3.stages;
+      q.stages = c3.stages; q.lo_stages = c3.lo_stages;
       if (st->x3) launch_on<TC_BWD, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem);
       else launch_on<TC_BWD, false>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem); }
     if (st->simt_adam && !pl.graph) { simt_adam_only(e, a); return; }
@@ -873,7 +907,7 @@ void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_va
     auto* st = static_cast<TcState*>(e.tc);
     const CUtensorMap& Xk = which_x == 2 ? st->Xte_k : st->Xchunk_k;
     TcParams p = base_params(e);
-    p.n_cols = INFER_TILE; p.tmem_cols = INFER_TILE; p.stages = st->infer.stages;
+    p.n_cols = INFER_TILE; p.tmem_cols = INFER_TILE; p.stages = st->infer.stages; p.lo_stages = st->infer.lo_stages;
     p.rows_per_block_y = INFER_TILE;
     p.ldh = (int64_t)e.S * e.Hp;
     p.n_valid = (int)n_valid; p.training = 0; p.drop_thresh = 0;
