@@ -23,6 +23,7 @@
 // Warp roles (192 threads): warps 0-3 epilogue (warp w reads TMEM lanes 32w..32w+31), warp 4 TMA producer,
 // warp 5 MMA issuer.  smem ring of 32-wide K slabs, full/empty mbarriers, one tmem_full barrier.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "engine.h"
@@ -37,7 +38,9 @@ namespace {
 enum { TC_FWD1 = 0, TC_FWD2 = 1, TC_BWD = 2 };
 
 constexpr int TILE_M = 128;              // TMEM lanes = output features per CTA
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 192;        // warps 0-3 epilogue, 4 TMA, 5 MMA
+constexpr int NTHREADS_X3 = 320;     // ... plus warps 6-9: extra residual converters (8 converter warps with 0-3)
+constexpr int NCONV = 256;           // converter threads of an X3 CTA
 constexpr int MAX_STAGES = 6;
 constexpr uint32_t A_STAGE_BYTES = TILE_M * BLOCK_K * 4;       // 16 KB
 
@@ -82,7 +85,15 @@ struct TcParams {
     // and Adam's bias-corrected rate is lr_table[step]
     const uint32_t* step_base;
     const float* lr_table;
+    // debugging (DEEPIMPUTE_B200_TRACE=1): CTA (0,0,0) records clock64() at pipeline events, 256 slots per kernel
+    unsigned long long* trace;
 };
+
+// DI_TRACE: for code run by ONE elected thread.  DI_TRACE_T0: for code run by whole warps -- thread 0 records and the
+// warp re-converges explicitly, because the .sync.aligned tcgen05 instructions that follow need all 32 lanes together
+// (a bare `if (threadIdx.x == 0)` in front of them left warp 0 diverged: launch failures and hung mbarriers).
+#define DI_TRACE(slot) do { if (p.trace && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x == 0) p.trace[(slot)] = clock64(); } while (0)
+#define DI_TRACE_T0(slot) do { if (p.trace && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x == 0) p.trace[(slot)] = clock64(); __syncwarp(); } while (0)
 
 __device__ __forceinline__ uint32_t dropout_step(const TcParams& p) { return p.step_base ? *p.step_base + p.step : p.step; }
 __device__ __forceinline__ AdamParams adam_of(const TcParams& p) {
@@ -117,7 +128,7 @@ __device__ __forceinline__ void softplus_sigmoid(float z, float& sp, float& sg) 
 // a_lo*b_hi + a_hi*b_lo + a_hi*b_hi into the same accumulator.  The dropped a_lo*b_lo term is 2^-20 relative, i.e.
 // fp32-level products on the tensor cores, at 3x the (negligible) MMA time and 2x the staging memory.
 template <int OP, bool X3>
-__global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                   const __grid_constant__ CUtensorMap mapB,
                                                                   const __grid_constant__ CUtensorMap mapC, const TcParams p) {
     constexpr bool A_MN = (OP != TC_BWD);
@@ -163,10 +174,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
     __shared__ double red[4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DI_TRACE_T0(0);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < lo_stages; ++i) { mbar_init(&lo_ready[i], 128); mbar_init(&lo_free[i], 1); }
+        for (int i = 0; i < lo_stages; ++i) { mbar_init(&lo_ready[i], NCONV); mbar_init(&lo_free[i], 1); }
         mbar_init(&tmem_full_bar, 1);
         mbar_init(&aux_bar, 1);
         fence_barrier_init();
@@ -177,6 +189,37 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
+    DI_TRACE_T0(1);
+
+    // residual pass (X3): lo = a - trunc19(a) for every float of the slab TMA just delivered, written to the next slab
+    // of the residual ring (element-wise: the swizzled layout carries over unchanged).  Run by 8 warps (0-3, 6-9).
+    auto convert = [&](int cid) {
+        const int per_thread = (int)(hi_bytes / 16) / NCONV;          // float4 per thread; hi_bytes is a multiple of 4 KB
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int st = kb % stages, ls = kb % lo_stages;
+            mbar_wait(&full_bar[st], (kb / stages) & 1, 1);
+            if (kb >= lo_stages) mbar_wait(&lo_free[ls], ((kb / lo_stages) - 1) & 1, 11);
+            const uint32_t hi = smem_u32(smem + (size_t)st * stage_bytes) + cid * 16;
+            const uint32_t lo = smem_u32(lo_base + (size_t)ls * stage_bytes) + cid * 16;
+            for (int i0 = 0; i0 < per_thread; i0 += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u < per_thread)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(hi + (i0 + u) * (NCONV * 16)));
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u < per_thread)
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
+                                     ::"r"(lo + (i0 + u) * (NCONV * 16)), "f"(tf32_residual(v[u].x)), "f"(tf32_residual(v[u].y)),
+                                       "f"(tf32_residual(v[u].z)), "f"(tf32_residual(v[u].w)) : "memory");
+            }
+            fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core
+            mbar_arrive(&lo_ready[ls]);
+            if (kb < 40) DI_TRACE_T0(128 + kb);
+        }
+    };
 
     if (warp == 4) {
         // ===== TMA producer =====
@@ -184,6 +227,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % stages;
                 if (kb >= stages) mbar_wait(&empty_bar[st], ((kb / stages) - 1) & 1, 2);
+                if (kb < 40) DI_TRACE(8 + kb);
                 uint8_t* sa = smem + (size_t)st * stage_bytes;
                 uint8_t* sb = sa + A_STAGE_BYTES;
                 mbar_arrive_expect_tx(&full_bar[st], hi_bytes);
@@ -204,8 +248,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
                 const int st = kb % stages;
                 mbar_wait(&full_bar[st], (kb / stages) & 1, 3);
                 const int ls = X3 ? kb % lo_stages : 0;
+                if (kb < 40) DI_TRACE(48 + kb);
                 if constexpr (X3) mbar_wait(&lo_ready[ls], (kb / lo_stages) & 1, 10);
                 tc_fence_after();
+                if (kb < 40) DI_TRACE(88 + kb);
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                 const uint32_t sb = sa + A_STAGE_BYTES;
                 if constexpr (X3) {
@@ -226,6 +272,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
             }
             umma_commit(&tmem_full_bar);
         }
+    } else if (warp >= 6) {
+        if constexpr (X3) convert((warp - 2) * 32 + lane);     // converter-only warps
     } else {
         // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = output features m0+32w.. =====
         const int fl = warp * 32 + lane;                  // feature inside the tile
@@ -233,37 +281,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
         const bool f_ok = f < out_dim;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
         const int ncol = p.n_cols;
-        if constexpr (X3) {
-            // residual pass: lo = a - trunc19(a) for every float of the slab TMA just delivered, written to the next
-            // slab of the residual ring (element-wise: the swizzled layout carries over unchanged)
-            const int per_thread = (int)(hi_bytes / 16) / 128;          // float4 per thread; hi_bytes is a multiple of 4 KB
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % stages, ls = kb % lo_stages;
-                mbar_wait(&full_bar[st], (kb / stages) & 1, 1);
-                if (kb >= lo_stages) mbar_wait(&lo_free[ls], ((kb / lo_stages) - 1) & 1, 11);
-                const uint32_t hi = smem_u32(smem + (size_t)st * stage_bytes) + threadIdx.x * 16;
-                const uint32_t lo = smem_u32(lo_base + (size_t)ls * stage_bytes) + threadIdx.x * 16;
-                for (int i0 = 0; i0 < per_thread; i0 += 4) {
-                    float4 v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (i0 + u < per_thread)
-                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                         : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(hi + (i0 + u) * 2048));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (i0 + u < per_thread)
-                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
-                                         ::"r"(lo + (i0 + u) * 2048), "f"(tf32_residual(v[u].x)), "f"(tf32_residual(v[u].y)),
-                                           "f"(tf32_residual(v[u].z)), "f"(tf32_residual(v[u].w)) : "memory");
-                }
-                fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core
-                mbar_arrive(&lo_ready[ls]);
-            }
-        }
+        if constexpr (X3) convert(warp * 32 + lane);
         if (p.aux_cols > 0) mbar_wait(&aux_bar, 0, 5);
+        DI_TRACE_T0(2);
         mbar_wait(&tmem_full_bar, 0, 4);
         tc_fence_after();
+        DI_TRACE_T0(3);
 
         if constexpr (OP == TC_FWD1) {
             const float bias = f_ok ? p.b1[(int64_t)s * p.Hp + f] : 0.f;
@@ -273,19 +296,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
             float* hlo = (p.training && p.Hlo) ? p.Hlo + (int64_t)s * p.Hp + f : nullptr;   // training h starts at row 0
             for (int c = 0; c < ncol; c += 16) {
                 float v[16];
+                __syncwarp();
                 tmem_ld16(taddr + c, v);
                 if (!f_ok) continue;
+                // four independent Philox calls first (instruction-level parallelism), then the 16 activations
+                uint32_t w[4][4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    uint32_t w[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-                    if (drop) dropout_words((uint32_t)f, (uint32_t)((c >> 2) + q), (uint32_t)d.gid, dstep, p.seed, w);
+                    w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0xFFFFFFFFu;
+                    if (drop) dropout_words((uint32_t)f, (uint32_t)((c >> 2) + q), (uint32_t)d.gid, dstep, p.seed, w[q]);
+                }
+                float a[16];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float a = fmaxf(v[4 * q + i] + bias, 0.f);
-                        if (drop) a = (w[i] >= p.drop_thresh) ? a * p.keep_scale : 0.f;
-                        hrow[(int64_t)(c + 4 * q + i) * p.ldh] = a;
-                        if (hlo) hlo[(int64_t)(c + 4 * q + i) * p.ldh] = tf32_residual(a);
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    a[i] = fmaxf(v[i] + bias, 0.f);
+                    if (drop) a[i] = (w[i >> 2][i & 3] >= p.drop_thresh) ? a[i] * p.keep_scale : 0.f;
+                }
+                float* dst = hrow + (int64_t)c * p.ldh;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[(int64_t)i * p.ldh] = a[i];
+                if (hlo) {
+                    float* dlo = hlo + (int64_t)c * p.ldh;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) dlo[(int64_t)i * p.ldh] = tf32_residual(a[i]);
                 }
             }
         } else if constexpr (OP == TC_FWD2) {
@@ -295,6 +328,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
             const int rows_left = p.n_valid - row_tile * ncol;
             for (int c = 0; c < ncol; c += 16) {
                 float v[16], y[16];
+                __syncwarp();
                 tmem_ld16(taddr + c, v);
                 if (!f_ok) continue;
                 if (p.aux_cols > 0) {
@@ -304,24 +338,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
 #pragma unroll
                     for (int i = 0; i < 16; ++i) y[i] = __ldg(p.Y + (row0 + c + i) * p.ldy + bi);
                 }
+                // phase 1: the 16 transcendental chains side by side (branch-free)
+                float yh[16], sg[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int b = c + i;
-                    const float z = v[i] + bias;
-                    float yhat, sg;
-                    softplus_sigmoid(z, yhat, sg);
-                    if (p.out) {
-                        if (b < rows_left && f < p.O)
-                            p.out[((int64_t)row_tile * ncol + b) * p.ld_out + (int64_t)s * p.O + f] = yhat;
-                    }
-                    if (p.Y) {
-                        const float diff = y[i] - yhat;
-                        part += y[i] * diff * diff;
-                        if (p.training) {
-                            const float g = 2.0f * y[i] * (yhat - y[i]) * sg * p.inv_norm;
-                            p.DZ2[(int64_t)b * p.S * p.Op + bi] = g;
-                            if (p.DZ2lo) p.DZ2lo[(int64_t)b * p.S * p.Op + bi] = tf32_residual(g);
-                            gsum += g;
+                for (int i = 0; i < 16; ++i) softplus_sigmoid(v[i] + bias, yh[i], sg[i]);
+                // phase 2: consumers
+                if (p.out && f < p.O) {
+                    float* dst = p.out + ((int64_t)row_tile * ncol + c) * p.ld_out + (int64_t)s * p.O + f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c + i < rows_left) dst[(int64_t)i * p.ld_out] = yh[i];
+                }
+                if (p.Y) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { const float diff = y[i] - yh[i]; part += y[i] * diff * diff; }
+                    if (p.training) {
+                        float g[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { g[i] = 2.0f * y[i] * (yh[i] - y[i]) * sg[i] * p.inv_norm; gsum += g[i]; }
+                        const int64_t ld2 = (int64_t)p.S * p.Op;
+                        float* dst = p.DZ2 + (int64_t)c * ld2 + bi;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dst[(int64_t)i * ld2] = g[i];
+                        if (p.DZ2lo) {
+                            float* dlo = p.DZ2lo + (int64_t)c * ld2 + bi;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) dlo[(int64_t)i * ld2] = tf32_residual(g[i]);
                         }
                     }
                 }
@@ -340,6 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
             float gsum = 0.f;
             for (int c = 0; c < ncol; c += 16) {
                 float v[16], h[16];
+                __syncwarp();
                 tmem_ld16(taddr + c, v);
                 if (!f_ok) continue;
                 if (p.aux_cols > 0) {
@@ -349,21 +392,28 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_kernel(const __grid_constant__
 #pragma unroll
                     for (int i = 0; i < 16; ++i) h[i] = p.Hact[(int64_t)(c + i) * p.S * p.Hp + bi];
                 }
+                float g[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float g = (h[i] > 0.f) ? v[i] * p.keep_scale : 0.f;
-                    p.DZ1[(int64_t)(c + i) * p.S * p.Hp + bi] = g;
-                    if (p.DZ1lo) p.DZ1lo[(int64_t)(c + i) * p.S * p.Hp + bi] = tf32_residual(g);
-                    gsum += g;
+                for (int i = 0; i < 16; ++i) { g[i] = (h[i] > 0.f) ? v[i] * p.keep_scale : 0.f; gsum += g[i]; }
+                const int64_t ld1 = (int64_t)p.S * p.Hp;
+                float* dst = p.DZ1 + (int64_t)c * ld1 + bi;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[(int64_t)i * ld1] = g[i];
+                if (p.DZ1lo) {
+                    float* dlo = p.DZ1lo + (int64_t)c * ld1 + bi;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) dlo[(int64_t)i * ld1] = tf32_residual(g[i]);
                 }
             }
             if (f_ok) adam_update_fast(gsum, p.b1[bi], p.mb1[bi], p.vb1[bi], adam_of(p));
         }
     }
 
+    DI_TRACE_T0(4);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+    DI_TRACE_T0(5);
 }
 
 // ============================================================================================ ADAM (weight update)
@@ -506,6 +556,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
             const int st = c % ring;
             float* ws = stage_ptr(st);
             float g[AD_R];
+            __syncwarp();
             tmem_ld8(taddr + c * AD_R, g);
             mbar_wait(&wfull[st], (c / ring) & 1, 7);
             if (f_ok) {
@@ -553,6 +604,7 @@ struct TcState {
     uint32_t* d_step_base = nullptr;
     float* d_lr_table = nullptr;
     bool use_graph = true, graph_failed = false;
+    unsigned long long* d_trace = nullptr;                 // DEEPIMPUTE_B200_TRACE=1: 3 kernels x 256 slots
     int smem_adam = 0;
     bool x3 = false;                                       // forward GEMMs error-compensated (DI_MATH_TF32X3)
     bool x3_bwd = false, simt_adam = false;                // experiments (DEEPIMPUTE_B200_EXPERIMENT bit 0 / bit 1)
@@ -602,7 +654,7 @@ template <int OP, bool X3>
 void launch(Engine& e, const char* name, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
             const TcParams& p, dim3 grid, int smem) {
     KernelTimer t(e, name);
-    tc_kernel<OP, X3><<<grid, NTHREADS, smem, e.stream>>>(a, b, c, p);
+    tc_kernel<OP, X3><<<grid, X3 ? NTHREADS_X3 : NTHREADS, smem, e.stream>>>(a, b, c, p);
     count_launch(e, name);
 }
 
@@ -685,6 +737,10 @@ bool tc_init(Engine& e) {
         for (int k = 0; k < 3; ++k)
             if (cudaEventCreateWithFlags(&st->gev[g][k], cudaEventDisableTiming) != cudaSuccess) { e.err = "cudaEventCreate failed"; return false; }
     }
+    if (const char* v = getenv("DEEPIMPUTE_B200_TRACE")) {
+        if (atoi(v) && cudaMalloc((void**)&st->d_trace, 3 * 256 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(st->d_trace, 0, 3 * 256 * sizeof(unsigned long long));
+    }
     if (cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc((void**)&st->d_step_base, sizeof(uint32_t)) != cudaSuccess) { e.err = "epoch-graph set-up failed"; return false; }
     const int nkb = e.Bp / BLOCK_K;
@@ -721,6 +777,7 @@ void tc_destroy(Engine& e) {
         }
         if (st->ev_fork) cudaEventDestroy(st->ev_fork);
         if (st->d_step_base) cudaFree(st->d_step_base);
+        if (st->d_trace) cudaFree(st->d_trace);
         if (st->d_lr_table) cudaFree(st->d_lr_table);
     }
     delete st;
@@ -759,9 +816,9 @@ struct StepPlan {
 template <int OP, bool X3>
 void launch_on(Engine& e, const StepPlan& pl, const char* name, const CUtensorMap& a, const CUtensorMap& b,
                const CUtensorMap& c, const TcParams& p, dim3 grid, int smem) {
-    if (pl.graph) { tc_kernel<OP, X3><<<grid, NTHREADS, smem, pl.main>>>(a, b, c, p); return; }
+    if (pl.graph) { tc_kernel<OP, X3><<<grid, X3 ? NTHREADS_X3 : NTHREADS, smem, pl.main>>>(a, b, c, p); return; }
     KernelTimer t(e, name);
-    tc_kernel<OP, X3><<<grid, NTHREADS, smem, pl.main>>>(a, b, c, p);
+    tc_kernel<OP, X3><<<grid, X3 ? NTHREADS_X3 : NTHREADS, smem, pl.main>>>(a, b, c, p);
     count_launch(e, name);
 }
 
@@ -789,16 +846,16 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     // writes W2, which FWD2 reads: the new step starts when it is done (ADAM2 therefore overlaps ADAM1 only)
     if (pl.side && !pl.first) cudaStreamWaitEvent(pl.main, pl.ev_adam2, 0);
     { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
-      q.stages = c1.stages; q.lo_stages = c1.lo_stages;
+      q.stages = c1.stages; q.lo_stages = c1.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace;
       if (st->x3) launch_on<TC_FWD1, true>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem);
       else launch_on<TC_FWD1, false>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem); }
     { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
-      q.stages = c2.stages; q.lo_stages = c2.lo_stages;
+      q.stages = c2.stages; q.lo_stages = c2.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 256;
       if (c2.aux) { q.aux_cols = st->aux_y; q.aux_row0 = a.row0; }
       if (st->x3) launch_on<TC_FWD2, true>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem);
       else launch_on<TC_FWD2, false>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem); }
     { TcParams q = p; q.m_tiles = mh; q.row0 = 0; q.aux_cols = st->aux_h; q.aux_row0 = 0;
-      q.stages = c3.stages; q.lo_stages = c3.lo_stages;
+      q.stages = c3.stages; q.lo_stages = c3.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 512;
       if (st->x3) launch_on<TC_BWD, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem);
       else launch_on<TC_BWD, false>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem); }
     if (st->simt_adam && !pl.graph) { simt_adam_only(e, a); return; }
@@ -885,7 +942,29 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
     auto* st = static_cast<TcState*>(e.tc);
     StepPlan pl;
     pl.s0 = 0; pl.ns = e.S; pl.main = e.stream;
+    if (const char* v = getenv("DEEPIMPUTE_B200_DEEP")) pl.deep = atoi(v) != 0;
     launch_step(e, st, a, which_x, pl);
+    if (st->d_trace && which_x == 1) {          // explicit-batch step: dump the pipeline trace of CTA (0,0,0)
+        static unsigned long long h[3 * 256];
+        cudaStreamSynchronize(e.stream);
+        cudaMemcpy(h, st->d_trace, sizeof h, cudaMemcpyDeviceToHost);
+        const char* names[3] = {"fwd1", "fwd2", "bwd"};
+        for (int k = 0; k < 3; ++k) {
+            const unsigned long long* t = h + 256 * k; const unsigned long long t0 = t[0];
+            fprintf(stderr, "[trace %s] prologue %llu | aux/tmem wait begins %llu | accumulator ready %llu | epilogue done %llu | exit %llu (cycles from CTA start)\n",
+                    names[k], t[1] - t0, t[2] - t0, t[3] - t0, t[4] - t0, t[5] - t0);
+            fprintf(stderr, "   kb: tma-issue  mma-slab-ready  mma-lo-ready  conv-done | converter: start  slab-ok  lo-free  converted  fenced\n");
+            for (int kb = 0; kb < 40 && t[8 + kb]; ++kb) {
+                fprintf(stderr, "   %2d: %9llu %9llu %9llu %9llu", kb, t[8 + kb] - t0, t[48 + kb] - t0, t[88 + kb] - t0,
+                        t[128 + kb] ? t[128 + kb] - t0 : 0ull);
+                if (kb < 16 && t[168 + 5 * kb])
+                    fprintf(stderr, " | %9llu %9llu %9llu %9llu %9llu", t[168 + 5 * kb] - t0, t[169 + 5 * kb] - t0,
+                            t[170 + 5 * kb] - t0, t[171 + 5 * kb] - t0, t[172 + 5 * kb] - t0);
+                fprintf(stderr, "\n");
+            }
+        }
+        cudaMemset(st->d_trace, 0, sizeof h);
+    }
 }
 
 bool tc_train_epoch_graph(Engine& e, int64_t first_step, const float* lr_t, int64_t n_steps) {
