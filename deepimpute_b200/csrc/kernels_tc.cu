@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DI_TRACE_T0(0);
     if (threadIdx.x == 0) {
         mbar_init(&ops_bar, 1); mbar_init(&mma_bar, 1); mbar_init(&tmem_full_bar, 1);
         for (int i = 0; i < ring; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wdone[i], 128); }
@@ -515,14 +516,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
                 const int st = c % ring;
                 float* ws = stage_ptr(st);
                 mbar_wait(&wdone[st], (c / ring) & 1, 8);           // all 128 epilogue threads updated this chunk
+                if (c < 40) DI_TRACE(48 + c);
                 const int32_t r = (int32_t)(row_base + n0 + c * AD_R);
                 tma_store_2d(&mapW, ws, m0, r);
                 tma_store_2d(&mapM, ws + tile_floats, m0, r);
                 tma_store_2d(&mapV, ws + 2 * tile_floats, m0, r);
                 bulk_commit();
-                if (c + ring < nchunks) {
-                    bulk_wait_read<0>();                         // the stores have read the stage: refill it
-                    load_chunk(c + ring);
+                // refill one iteration late: by now the PREVIOUS chunk's stores have read their stage, so the wait
+                // does not stall this thread (it only has to keep the most recent group in flight)
+                if (c >= 1 && c - 1 + ring < nchunks) {
+                    bulk_wait_read<1>();
+                    load_chunk(c - 1 + ring);
                 }
             }
             bulk_wait<0>();
@@ -550,8 +554,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
         const bool f_ok = (m0 + fl) < out_dim;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
         const AdamParams adam = adam_of(p);
+        DI_TRACE_T0(2);
         mbar_wait(&tmem_full_bar, 0, 4);
         tc_fence_after();
+        DI_TRACE_T0(3);
         for (int c = 0; c < nchunks; ++c) {
             const int st = c % ring;
             float* ws = stage_ptr(st);
@@ -559,23 +565,38 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
             __syncwarp();
             tmem_ld8(taddr + c * AD_R, g);
             mbar_wait(&wfull[st], (c / ring) & 1, 7);
+            if (c < 40) DI_TRACE_T0(8 + c);
             if (f_ok) {
+                // all 24 loads, then 8 independent updates, then all 24 stores: written with shared-space
+                // instructions on explicit register arrays so that no store can alias (and serialise) a later load
+                const uint32_t base = smem_u32(ws) + (uint32_t)fl * 4u;
+                const uint32_t row_b = (uint32_t)wbox * 4u, tile_b = (uint32_t)tile_floats * 4u;
+                float w[AD_R], m[AD_R], v[AD_R];
 #pragma unroll
                 for (int r = 0; r < AD_R; ++r) {
-                    const int idx = r * wbox + fl;
-                    float w = ws[idx], m = ws[tile_floats + idx], v = ws[2 * tile_floats + idx];
-                    adam_update_fast(g[r], w, m, v, adam);
-                    ws[idx] = w; ws[tile_floats + idx] = m; ws[2 * tile_floats + idx] = v;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[r]) : "r"(base + r * row_b));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m[r]) : "r"(base + tile_b + r * row_b));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[r]) : "r"(base + 2 * tile_b + r * row_b));
+                }
+#pragma unroll
+                for (int r = 0; r < AD_R; ++r) adam_update_fast(g[r], w[r], m[r], v[r], adam);
+#pragma unroll
+                for (int r = 0; r < AD_R; ++r) {
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + r * row_b), "f"(w[r]) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + tile_b + r * row_b), "f"(m[r]) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 2 * tile_b + r * row_b), "f"(v[r]) : "memory");
                 }
             }
             fence_proxy_async();                          // generic-proxy writes -> visible to the TMA store
             mbar_arrive(&wdone[st]);
         }
+        DI_TRACE_T0(4);
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+    DI_TRACE_T0(5);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -738,8 +759,8 @@ bool tc_init(Engine& e) {
             if (cudaEventCreateWithFlags(&st->gev[g][k], cudaEventDisableTiming) != cudaSuccess) { e.err = "cudaEventCreate failed"; return false; }
     }
     if (const char* v = getenv("DEEPIMPUTE_B200_TRACE")) {
-        if (atoi(v) && cudaMalloc((void**)&st->d_trace, 3 * 256 * sizeof(unsigned long long)) == cudaSuccess)
-            cudaMemset(st->d_trace, 0, 3 * 256 * sizeof(unsigned long long));
+        if (atoi(v) && cudaMalloc((void**)&st->d_trace, 5 * 256 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(st->d_trace, 0, 5 * 256 * sizeof(unsigned long long));
     }
     if (cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc((void**)&st->d_step_base, sizeof(uint32_t)) != cudaSuccess) { e.err = "epoch-graph set-up failed"; return false; }
@@ -864,7 +885,7 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     const CUtensorMap& Xlo = which_x == 0 ? st->Xtr_lo_mn : st->Xstep_lo_mn;
     cudaStream_t s2 = pl.side ? pl.side : pl.main;
     if (pl.side) { cudaEventRecord(pl.ev_bwd, pl.main); cudaStreamWaitEvent(pl.side, pl.ev_bwd, 0); }
-    { q.which = 2; q.row0 = 0; q.wbox = st->wbox2;
+    { q.which = 2; q.row0 = 0; q.wbox = st->wbox2; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 768;
       const dim3 grid(cdiv(e.Hp, ADAM_TILE), mo, pl.ns);
       KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam2");
       if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, s2>>>(
@@ -873,7 +894,7 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
           st->DZ2_mn, st->H_mn, st->DZ2_mn, st->H_mn, st->W2_t[0], st->W2_t[1], st->W2_t[2], q);
       if (t) { delete t; count_launch(e, "adam2"); } }
     if (pl.side) cudaEventRecord(pl.ev_adam2, pl.side);
-    { q.which = 1; q.row0 = a.row0; q.wbox = st->wbox1;
+    { q.which = 1; q.row0 = a.row0; q.wbox = st->wbox1; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 1024;
       int maxPp = 0;
       for (int s = pl.s0; s < pl.s0 + pl.ns; ++s) maxPp = std::max(maxPp, e.Pp[s]);
       const dim3 grid(cdiv(maxPp, ADAM_TILE), mh, pl.ns);
@@ -945,7 +966,7 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
     if (const char* v = getenv("DEEPIMPUTE_B200_DEEP")) pl.deep = atoi(v) != 0;
     launch_step(e, st, a, which_x, pl);
     if (st->d_trace && which_x == 1) {          // explicit-batch step: dump the pipeline trace of CTA (0,0,0)
-        static unsigned long long h[3 * 256];
+        static unsigned long long h[5 * 256];
         cudaStreamSynchronize(e.stream);
         cudaMemcpy(h, st->d_trace, sizeof h, cudaMemcpyDeviceToHost);
         const char* names[3] = {"fwd1", "fwd2", "bwd"};
@@ -962,6 +983,14 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
                             t[170 + 5 * kb] - t0, t[171 + 5 * kb] - t0, t[172 + 5 * kb] - t0);
                 fprintf(stderr, "\n");
             }
+        }
+        for (int k = 3; k < 5; ++k) {
+            const unsigned long long* t = h + 256 * k; const unsigned long long t0 = t[0];
+            fprintf(stderr, "[trace %s] epilogue waits for accumulator from %llu | accumulator ready %llu | last chunk done %llu | exit %llu\n",
+                    k == 3 ? "adam2" : "adam1", t[2] - t0, t[3] - t0, t[4] - t0, t[5] - t0);
+            fprintf(stderr, "   chunk: tile-in-smem  updated(store issued)\n");
+            for (int c = 0; c < 40 && t[8 + c]; ++c)
+                fprintf(stderr, "   %2d: %9llu %9llu\n", c, t[8 + c] - t0, t[48 + c] ? t[48 + c] - t0 : 0ull);
         }
         cudaMemset(st->d_trace, 0, sizeof h);
     }
