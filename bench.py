@@ -185,11 +185,24 @@ def load_peaks():
     return dict(hbm=6650.0, tensor=1590.0, source="fallback")
 
 
-def load_traffic(workload, kernel):
-    """dram bytes per launch of ``kernel`` from the committed ncu capture (profiles/traffic.json), or None."""
+def load_traffic(workload, kernel, n_pred):
+    """dram bytes per launch of ``kernel`` from the committed ncu capture (profiles/traffic.json, written by
+    scripts/summarise_profile.py from an ``ncu --set full`` run of this same command), or None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
-        return json.load(open(path)).get(workload, {}).get(kernel)
+    if not os.path.exists(path):
+        return None
+    S, cd = len(n_pred), lambda a, b: -(-a // b)
+    max_pp = max(cd(p, 32) * 32 for p in n_pred)
+    grids = {"adam2": (cd(HIDDEN, 128), cd(OUT, 128), S), "adam1": (cd(max_pp, 128), cd(HIDDEN, 128), S),
+             "fwd1": (1, cd(HIDDEN, 128), S), "fwd2": (1, cd(OUT, 128), S), "bwd": (1, cd(HIDDEN, 128), S)}
+    names = {"adam2": "tc_adam_kernel", "adam1": "tc_adam_kernel", "fwd1": "tc_kernel<0", "fwd2": "tc_kernel<1",
+             "bwd": "tc_kernel<2"}
+    if kernel not in grids:
+        return None
+    want = "grid ({}, {}, {})".format(*grids[kernel])
+    for key, val in json.load(open(path)).get(workload, {}).items():
+        if key.startswith(names[kernel]) and key.endswith(want):
+            return val
     return None
 
 
@@ -422,7 +435,7 @@ def main():
         step_ms = sum(per_kernel[k]["ms"] for k in train_kernels)
         roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peaks["hbm"],
                     "unit": "GB/s", "frac": round(achieved / peaks["hbm"], 4),
-                    "traffic": load_traffic(wl["name"], top), "peak_source": peaks["source"],
+                    "traffic": load_traffic(wl["name"], top, n_pred), "peak_source": peaks["source"],
                     "algorithmic_bytes_per_launch": work[top]["bytes"],
                     "train_step": {"ms": round(step_ms, 4), "GB/s": round(step_bytes / (step_ms * 1e-3) / 1e9, 1),
                                    "frac": round(step_bytes / (step_ms * 1e-3) / 1e9 / peaks["hbm"], 4),
@@ -438,6 +451,8 @@ def main():
                        "predictors_per_subnet": [int(min(n_pred_all)), int(max(n_pred_all))],
                        "adam_steps_per_epoch": steps_per_epoch, "math_mode": math_mode,
                        "parallelism": "sub-networks sharded over {} GPU(s)".format(world),
+                       "epoch_driver": "one CUDA-graph launch per epoch over sub-network groups on concurrent streams; "
+                                       "roofline.kernels are timed in a separate launch-by-launch epoch",
                        "l2": "inputs larger than L2: {:.1f} GB of weights+Adam state+staged batches stream per epoch"
                              .format((step_bytes * steps_per_epoch) / 1e9)},
             "clocks": clocks.summary(),
