@@ -445,7 +445,7 @@ def main():
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32 (3-pass forward)"}[math_mode], "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3 (error-compensated TF32, fp32 accumulate)"}[math_mode], "data": "synthetic",
             "config": {"workload": wl["desc"], "epochs_per_step": args.epochs, "batch_size": B,
                        "sub_networks": S_all, "hidden": HIDDEN, "sub_outputdim": OUT,
                        "predictors_per_subnet": [int(min(n_pred_all)), int(max(n_pred_all))],

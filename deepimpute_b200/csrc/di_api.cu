@@ -332,6 +332,7 @@ int di_upload_matrix(di_handle* h, const float* norm, int64_t n_cells, int64_t n
         e.N = n_cells; e.G = n_genes;
     }
     DI_CUDA(cudaMemcpyAsync(e.d_norm, norm, (size_t)n_cells * n_genes * sizeof(float), cudaMemcpyHostToDevice, e.stream));
+    e.split_stale = true;           // staged train / test matrices (if any) hold values of the previous matrix
     return sync_check(e);
 }
 
@@ -359,8 +360,9 @@ int di_set_partition(di_handle* h, const int32_t* pred_idx, const int64_t* pred_
     DI_CUDA(cudaMemcpyAsync(e.d_targ_cols, tc.data(), tc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
     int rc = sync_check(e);
     e.have_partition = rc == DI_OK;
-    // a new partition invalidates staged train/test matrices
-    if (e.n_train || e.n_test) free_split(e);
+    // a new partition invalidates the CONTENTS of the staged train/test matrices; the buffers (and everything bound
+    // to their addresses: tensor maps, the epoch graph) are kept and refilled by the next di_set_split
+    e.split_stale = true;
     return rc;
 }
 
@@ -374,26 +376,30 @@ int di_set_split(di_handle* h, const int32_t* train_rows, int64_t n_train, const
     for (int64_t i = 0; i < n_test; ++i) if (test_rows[i] < 0 || test_rows[i] >= e.N) return fail(e, DI_ERR_ARG, "di_set_split: test row out of range");
     DI_CUDA(cudaSetDevice(e.cfg.device));
     DI_CUDA(cudaStreamSynchronize(e.stream));
-    free_split(e);
     const int64_t ldy = (int64_t)e.S * e.Op;
-    e.n_train = n_train; e.n_test = n_test;
-    e.n_train_pad = std::max<int64_t>((n_train + e.B - 1) / e.B, 1) * e.Bp;
-    e.n_test_pad = round_up64(std::max<int64_t>(n_test, 1), 128);
+    // same geometry as the staged split: keep the buffers, so tensor maps and the captured epoch graph stay valid
+    const bool reuse = e.Xtr && e.Xte && n_train == e.n_train && n_test == e.n_test;
     int rc;
-    if ((rc = dev_alloc(e, &e.d_train_rows, std::max<int64_t>(n_train, 1)))) return rc;
-    if ((rc = dev_alloc(e, &e.d_perm, std::max<int64_t>(n_train, 1)))) return rc;
-    if ((rc = dev_alloc(e, &e.d_test_rows, std::max<int64_t>(n_test, 1)))) return rc;
-    if ((rc = dev_alloc(e, &e.Xtr, e.n_train_pad * e.PT, false))) return rc;
-    if (e.cfg.math_mode == DI_MATH_TF32X3 && (rc = dev_alloc(e, &e.Xtr_lo, e.n_train_pad * e.PT, false))) return rc;
-    if ((rc = dev_alloc(e, &e.Ytr, e.n_train_pad * ldy, false))) return rc;
-    if ((rc = dev_alloc(e, &e.Xte, e.n_test_pad * e.PT, false))) return rc;
-    if ((rc = dev_alloc(e, &e.Yte, e.n_test_pad * ldy, false))) return rc;
+    if (!reuse) {
+        free_split(e);
+        e.n_train = n_train; e.n_test = n_test;
+        e.n_train_pad = std::max<int64_t>((n_train + e.B - 1) / e.B, 1) * e.Bp;
+        e.n_test_pad = round_up64(std::max<int64_t>(n_test, 1), 128);
+        if ((rc = dev_alloc(e, &e.d_train_rows, std::max<int64_t>(n_train, 1)))) return rc;
+        if ((rc = dev_alloc(e, &e.d_perm, std::max<int64_t>(n_train, 1)))) return rc;
+        if ((rc = dev_alloc(e, &e.d_test_rows, std::max<int64_t>(n_test, 1)))) return rc;
+        if ((rc = dev_alloc(e, &e.Xtr, e.n_train_pad * e.PT, false))) return rc;
+        if (e.cfg.math_mode == DI_MATH_TF32X3 && (rc = dev_alloc(e, &e.Xtr_lo, e.n_train_pad * e.PT, false))) return rc;
+        if ((rc = dev_alloc(e, &e.Ytr, e.n_train_pad * ldy, false))) return rc;
+        if ((rc = dev_alloc(e, &e.Xte, e.n_test_pad * e.PT, false))) return rc;
+        if ((rc = dev_alloc(e, &e.Yte, e.n_test_pad * ldy, false))) return rc;
+    }
+    e.split_stale = false;
     if (n_train) DI_CUDA(cudaMemcpyAsync(e.d_train_rows, train_rows, n_train * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
     if (n_test) DI_CUDA(cudaMemcpyAsync(e.d_test_rows, test_rows, n_test * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
     // held-out matrices are staged once; training matrices are re-gathered in shuffled order every epoch
-    launch_gather(e, e.d_test_rows, nullptr, 0, e.n_test_pad, n_test, e.d_pred_cols, e.PT, e.Xte);
-    launch_gather(e, e.d_test_rows, nullptr, 0, e.n_test_pad, n_test, e.d_targ_cols, ldy, e.Yte);
-    if (e.cfg.math_mode != DI_MATH_FP32 && !tc_rebind(e)) return DI_ERR_CUDA;
+    launch_gather_xy(e, e.d_test_rows, nullptr, e.n_test_pad, n_test, 0, 0, e.Xte, nullptr, e.Yte);
+    if (!reuse && e.cfg.math_mode != DI_MATH_FP32 && !tc_rebind(e)) return DI_ERR_CUDA;
     return sync_check(e);
 }
 
@@ -465,8 +471,7 @@ int di_train_step(di_handle* h, const int32_t* rows, int32_t nrows, int64_t step
     DI_CUDA(cudaMemcpyAsync(e.d_step_rows, rows, nrows * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
     DI_CUDA(cudaEventRecord(e.ev0, e.stream));
     DI_CUDA(cudaMemsetAsync(e.d_loss, 0, sizeof(double), e.stream));
-    launch_gather(e, e.d_step_rows, nullptr, 0, e.Bp, nrows, e.d_pred_cols, e.PT, e.Xstep, 0, 0, e.Xstep_lo);
-    launch_gather(e, e.d_step_rows, nullptr, 0, e.Bp, nrows, e.d_targ_cols, (int64_t)e.S * e.Op, e.Ystep);
+    launch_gather_xy(e, e.d_step_rows, nullptr, e.Bp, nrows, 0, 0, e.Xstep, e.Xstep_lo, e.Ystep);
     int rc = run_step(e, e.Xstep, e.Ystep, 0, nrows, step, 1);
     if (rc) return rc;
     DI_CUDA(cudaEventRecord(e.ev1, e.stream));
@@ -480,7 +485,7 @@ int di_train_step(di_handle* h, const int32_t* rows, int32_t nrows, int64_t step
 int di_validation_loss(di_handle* h, float* val_loss_out) {
     if (!h) return DI_ERR_ARG;
     Engine& e = h->e;
-    if (!e.Xte) return fail(e, DI_ERR_ARG, "di_validation_loss: call di_set_split first");
+    if (!e.Xte || e.split_stale) return fail(e, DI_ERR_ARG, "di_validation_loss: call di_set_split first");
     DI_CUDA(cudaSetDevice(e.cfg.device));
     int rc = validation_pass(e);
     if (rc) return rc;
@@ -493,7 +498,7 @@ int di_validation_loss(di_handle* h, float* val_loss_out) {
 int di_train_epoch(di_handle* h, const int32_t* perm, int64_t first_step, float* loss_out, float* val_loss_out) {
     if (!h) return DI_ERR_ARG;
     Engine& e = h->e;
-    if (!e.Xtr || e.n_train <= 0) return fail(e, DI_ERR_ARG, "di_train_epoch: call di_set_split first");
+    if (!e.Xtr || e.n_train <= 0 || e.split_stale) return fail(e, DI_ERR_ARG, "di_train_epoch: call di_set_split first");
     if (!perm || first_step < 0) return fail(e, DI_ERR_ARG, "di_train_epoch: bad arguments");
     for (int64_t i = 0; i < e.n_train; ++i) if (perm[i] < 0 || perm[i] >= e.n_train) return fail(e, DI_ERR_ARG, "di_train_epoch: perm out of range");
     DI_CUDA(cudaSetDevice(e.cfg.device));
@@ -502,8 +507,7 @@ int di_train_epoch(di_handle* h, const int32_t* perm, int64_t first_step, float*
     DI_CUDA(cudaEventRecord(e.ev0, e.stream));
     DI_CUDA(cudaMemsetAsync(e.d_loss, 0, 2 * sizeof(double), e.stream));
     // stage this epoch's visiting order: batch i is rows [i*B, (i+1)*B) of Xtr / Ytr
-    launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_pred_cols, e.PT, e.Xtr, e.B, e.Bp, e.Xtr_lo);
-    launch_gather(e, e.d_train_rows, e.d_perm, 0, e.n_train_pad, e.n_train, e.d_targ_cols, ldy, e.Ytr, e.B, e.Bp);
+    launch_gather_xy(e, e.d_train_rows, e.d_perm, e.n_train_pad, e.n_train, e.B, e.Bp, e.Xtr, e.Xtr_lo, e.Ytr);
     const int64_t n_steps = (e.n_train + e.B - 1) / e.B;
     bool graphed = false;
     if (e.cfg.math_mode != DI_MATH_FP32 && !e.profiling) {

@@ -46,6 +46,7 @@ struct Engine {
     int32_t* d_pred_cols = nullptr; // [PT]   gene column of every packed X column, -1 = padding
     int32_t* d_targ_cols = nullptr; // [S*Op] gene column of every packed Y column, -1 = padding
     bool have_partition = false;
+    bool split_stale = false;       // partition changed since di_set_split: staged matrices must be refilled
 
     float *W1 = nullptr, *mW1 = nullptr, *vW1 = nullptr;
     float *b1 = nullptr, *mb1 = nullptr, *vb1 = nullptr;
@@ -99,6 +100,12 @@ struct Engine {
 void launch_gather(Engine& e, const int32_t* rows, const int32_t* perm, int64_t first_row, int64_t n_out,
                    int64_t n_valid, const int32_t* cols, int64_t width, float* out, int batch = 0, int batch_pitch = 0,
                    float* out_lo = nullptr);
+
+// Predictor AND target matrices of the same rows in one pass: every source row of norm is staged once in shared
+// memory (coalesced read), both packed outputs are gathered from there (coalesced writes).  X -> [n_out][PT] (+ its
+// TF32 residual twin when X_lo != nullptr), Y -> [n_out][S*Op].  Row mapping as in launch_gather.
+void launch_gather_xy(Engine& e, const int32_t* rows, const int32_t* perm, int64_t n_out, int64_t n_valid,
+                      int batch, int batch_pitch, float* X, float* X_lo, float* Y);
 
 // ---- fp32 CUDA-core path (kernels_simt.cu) -------------------------------------------------------------------
 void simt_train_step(Engine& e, const StepArgs& a);

@@ -245,6 +245,54 @@ __global__ void gather_kernel(const float* __restrict__ norm, int64_t G, const i
     }
 }
 
+// One block per output row (grid-stride): the whole source row of norm goes through shared memory once.
+__global__ void __launch_bounds__(512) gather_xy_kernel(const float* __restrict__ norm, int64_t G, const int32_t* __restrict__ rows,
+                                                        const int32_t* __restrict__ perm, int64_t n_out, int64_t n_valid,
+                                                        int batch, int batch_pitch,
+                                                        const int32_t* __restrict__ xcols, int64_t xw, float* __restrict__ X,
+                                                        float* __restrict__ X_lo,
+                                                        const int32_t* __restrict__ ycols, int64_t yw, float* __restrict__ Y) {
+    extern __shared__ float srow[];
+    for (int64_t io = blockIdx.x; io < n_out; io += gridDim.x) {
+        int64_t i = io;
+        bool valid = io < n_valid;
+        if (batch > 0) {
+            const int64_t r = io % batch_pitch;
+            i = (io / batch_pitch) * batch + r;
+            valid = r < batch && i < n_valid;
+        }
+        float* xd = X + io * xw;
+        float* xl = X_lo ? X_lo + io * xw : nullptr;
+        float* yd = Y + io * yw;
+        if (!valid) {                                   // padding row (uniform per block)
+            for (int64_t j = threadIdx.x; j < xw; j += blockDim.x) { xd[j] = 0.f; if (xl) xl[j] = 0.f; }
+            for (int64_t j = threadIdx.x; j < yw; j += blockDim.x) yd[j] = 0.f;
+            continue;
+        }
+        const int64_t r = (int64_t)rows[perm ? perm[i] : i];
+        const float* src = norm + r * G;
+        __syncthreads();                                // previous row fully consumed
+        if ((G & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(srow);
+            for (int64_t j = threadIdx.x; j < (G >> 2); j += blockDim.x) d4[j] = __ldg(s4 + j);
+        } else {
+            for (int64_t j = threadIdx.x; j < G; j += blockDim.x) srow[j] = __ldg(src + j);
+        }
+        __syncthreads();
+        for (int64_t j = threadIdx.x; j < xw; j += blockDim.x) {
+            const int32_t c = xcols[j];
+            const float v = (c >= 0) ? srow[c] : 0.f;
+            xd[j] = v;
+            if (xl) xl[j] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        }
+        for (int64_t j = threadIdx.x; j < yw; j += blockDim.x) {
+            const int32_t c = ycols[j];
+            yd[j] = (c >= 0) ? srow[c] : 0.f;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ bias + Adam
 // db2[s][o] = sum_b DZ2[b][s*Op+o],  db1[s][h] = sum_b DZ1[b][s*Hp+h]; one thread per bias element.
 __global__ void bias_adam_kernel(const float* __restrict__ DZ2, const float* __restrict__ DZ1, int rows,
@@ -287,6 +335,30 @@ void launch_gather(Engine& e, const int32_t* rows, const int32_t* perm, int64_t 
     dim3 grid((unsigned)std::min<int64_t>((width + 255) / 256, 64), (unsigned)std::min<int64_t>(n_out, 16384));
     gather_kernel<<<grid, 256, 0, e.stream>>>(e.d_norm, e.G, rows, perm, first_row, n_out, n_valid, cols, width, out,
                                               batch, batch_pitch, out_lo);
+    count_launch(e, "gather");
+}
+
+void launch_gather_xy(Engine& e, const int32_t* rows, const int32_t* perm, int64_t n_out, int64_t n_valid,
+                      int batch, int batch_pitch, float* X, float* X_lo, float* Y) {
+    if (n_out <= 0) return;
+    const int64_t ldy = (int64_t)e.S * e.Op;
+    const size_t smem = (size_t)e.G * sizeof(float);
+    static int max_smem = -1;
+    if (max_smem < 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    if (!rows || smem > (size_t)max_smem) {             // row does not fit in shared memory: two plain gathers
+        launch_gather(e, rows, perm, 0, n_out, n_valid, e.d_pred_cols, e.PT, X, batch, batch_pitch, X_lo);
+        launch_gather(e, rows, perm, 0, n_out, n_valid, e.d_targ_cols, ldy, Y, batch, batch_pitch);
+        return;
+    }
+    KernelTimer t(e, "gather");
+    cudaFuncSetAttribute(gather_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int per_sm = std::max(1, std::min(4, (int)((size_t)max_smem / std::max<size_t>(smem, 1))));
+    const unsigned grid = (unsigned)std::min<int64_t>(n_out, (int64_t)148 * per_sm);
+    gather_xy_kernel<<<grid, 512, smem, e.stream>>>(e.d_norm, e.G, rows, perm, n_out, n_valid, batch, batch_pitch,
+                                                    e.d_pred_cols, e.PT, X, X_lo, e.d_targ_cols, ldy, Y);
     count_launch(e, "gather");
 }
 

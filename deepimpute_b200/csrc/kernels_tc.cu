@@ -613,12 +613,14 @@ struct TcState {
     CUtensorMap Xtr_k, Xtr_mn, Xte_k, Ytr_aux;
     bool have_split = false;
     struct Cfg { int stages = 0, lo_stages = 0, smem = 0; bool aux = false; };
-    Cfg fwd1_train[2], fwd2_train[2], bwd_train[2], infer;   // [0]: two CTAs per SM where possible, [1]: deepest ring
+    Cfg fwd1_train[3], fwd2_train[3], bwd_train[3], infer;   // [0]: two CTAs per SM where possible, [1]: deepest ring,
+                                                             // [2]: "medium": fits beside one ADAM CTA on the same SM
     // epoch graph over sub-network groups
     int n_groups = 1, group_deep = 0;
-    int group_s0[9] = {0};
-    cudaStream_t gstream[8][2] = {};
-    cudaEvent_t gev[8][3] = {};
+    static constexpr int MAX_GROUPS = 40;
+    int group_s0[MAX_GROUPS + 1] = {0};
+    cudaStream_t gstream[MAX_GROUPS][2] = {};
+    cudaEvent_t gev[MAX_GROUPS][3] = {};
     cudaEvent_t ev_fork = nullptr;
     cudaGraphExec_t epoch_exec = nullptr;
     int64_t graph_nodes = 0, graph_n_train = -1, lr_capacity = 0;
@@ -643,7 +645,7 @@ int smem_for(int n_cols, int stages, int lo_stages, int aux_floats) {
 }
 // deepest ring (<= MAX_STAGES) that still leaves room for two CTAs per SM; if even two stages do not fit in half an
 // SM, the deepest ring that fits in one
-TcState::Cfg pick_cfg(int n_cols, int aux_floats, bool x3, bool deep = false) {
+TcState::Cfg pick_cfg(int n_cols, int aux_floats, bool x3, bool deep = false, int only_budget = 0) {
     // (raw slabs, residual slabs) in order of preference; the first that fits the budget wins
     static const int plain[][2] = {{6, 0}, {5, 0}, {4, 0}, {3, 0}, {2, 0}};
     static const int comp[][2] = {{5, 3}, {4, 3}, {4, 2}, {3, 2}, {2, 2}, {2, 1}};
@@ -651,6 +653,7 @@ TcState::Cfg pick_cfg(int n_cols, int aux_floats, bool x3, bool deep = false) {
     c.aux = aux_floats > 0;
     for (int budget : {110 * 1024, 224 * 1024}) {
         if (deep && budget < 200 * 1024) continue;
+        if (only_budget) budget = only_budget;
         for (int i = 0; i < (x3 ? 6 : 5); ++i) {
             const int hs = x3 ? comp[i][0] : plain[i][0], ls = x3 ? comp[i][1] : 0;
             const int bytes = smem_for(n_cols, hs, ls, aux_floats);
@@ -741,17 +744,27 @@ bool tc_init(Engine& e) {
         st->fwd2_train[deep] = pick_cfg(e.Bp, (st->x3 && !deep) ? 0 : aux_floats, st->x3, deep);
         st->bwd_train[deep] = pick_cfg(e.Bp, aux_floats, st->x3, deep);
     }
+    // medium: leaves room for one ADAM CTA (its dynamic + static + reserved shared memory) on the same SM; no aux tile
+    {
+        const int nkb_a = e.Bp / BLOCK_K;
+        const int adam_bytes = nkb_a * (int)(A_STAGE_BYTES + ADAM_TILE * BLOCK_K * 4) + AD_STAGES * 3 * AD_R * TILE_M * 4 + 1024;
+        const int room = 228 * 1024 - (adam_bytes + 2048) - 2048;
+        st->fwd1_train[2] = pick_cfg(e.Bp, 0, st->x3, false, room);
+        st->fwd2_train[2] = pick_cfg(e.Bp, 0, st->x3, false, room);
+        st->bwd_train[2] = pick_cfg(e.Bp, 0, st->x3, false, room);
+        if (!st->fwd1_train[2].stages) { st->fwd1_train[2] = st->fwd1_train[0]; st->fwd2_train[2] = st->fwd2_train[0]; st->bwd_train[2] = st->bwd_train[0]; }
+    }
     st->infer = pick_cfg(INFER_TILE, 0, st->x3, true);
     // sub-network groups of the epoch graph: independent chains on their own streams
-    int G = std::min(4, e.S);
-    if (const char* v = getenv("DEEPIMPUTE_B200_GROUPS")) G = std::max(1, std::min(std::min(8, e.S), atoi(v)));
+    int G = std::min(16, e.S);
+    if (const char* v = getenv("DEEPIMPUTE_B200_GROUPS")) G = std::max(1, std::min(std::min((int)TcState::MAX_GROUPS, e.S), atoi(v)));
     if (const char* v = getenv("DEEPIMPUTE_B200_GRAPH")) st->use_graph = atoi(v) != 0;
     st->n_groups = G;
     for (int g = 0; g <= G; ++g) st->group_s0[g] = (int)((int64_t)e.S * g / G);
     // a group's forward / backward grids are small: when all of them fit one CTA per SM, use the deep rings
     const int per_group = (e.S + G - 1) / G;
     st->group_deep = (per_group * cdiv(e.Op, TILE_M) <= 148) ? 1 : 0;
-    if (const char* v = getenv("DEEPIMPUTE_B200_DEEP")) st->group_deep = atoi(v) != 0;
+    if (const char* v = getenv("DEEPIMPUTE_B200_DEEP")) st->group_deep = std::max(0, std::min(2, atoi(v)));
     for (int g = 0; g < G; ++g) {
         for (int k = 0; k < 2; ++k)
             if (cudaStreamCreateWithFlags(&st->gstream[g][k], cudaStreamNonBlocking) != cudaSuccess) { e.err = "cudaStreamCreate failed"; return false; }
@@ -771,9 +784,9 @@ bool tc_init(Engine& e) {
         e.err = "tensor-core math modes: this batch size needs more shared memory than one SM has (use math mode fp32)";
         return false;
     }
-    const int m1 = std::max(std::max(st->fwd1_train[0].smem, st->fwd1_train[1].smem), st->infer.smem);
-    const int m2 = std::max(std::max(st->fwd2_train[0].smem, st->fwd2_train[1].smem), st->infer.smem);
-    const int m3 = std::max(st->bwd_train[0].smem, st->bwd_train[1].smem);
+    const int m1 = std::max(std::max(std::max(st->fwd1_train[0].smem, st->fwd1_train[1].smem), st->fwd1_train[2].smem), st->infer.smem);
+    const int m2 = std::max(std::max(std::max(st->fwd2_train[0].smem, st->fwd2_train[1].smem), st->fwd2_train[2].smem), st->infer.smem);
+    const int m3 = std::max(std::max(st->bwd_train[0].smem, st->bwd_train[1].smem), st->bwd_train[2].smem);
     cudaError_t ce = cudaSuccess;
     auto set = [&](const void* fn, int bytes) {
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -792,7 +805,7 @@ void tc_destroy(Engine& e) {
     auto* st = static_cast<TcState*>(e.tc);
     if (st) {
         drop_epoch_graph(st);
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < TcState::MAX_GROUPS; ++g) {
             for (int k = 0; k < 2; ++k) if (st->gstream[g][k]) cudaStreamDestroy(st->gstream[g][k]);
             for (int k = 0; k < 3; ++k) if (st->gev[g][k]) cudaEventDestroy(st->gev[g][k]);
         }
@@ -875,7 +888,8 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
       if (c2.aux) { q.aux_cols = st->aux_y; q.aux_row0 = a.row0; }
       if (st->x3) launch_on<TC_FWD2, true>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem);
       else launch_on<TC_FWD2, false>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem); }
-    { TcParams q = p; q.m_tiles = mh; q.row0 = 0; q.aux_cols = st->aux_h; q.aux_row0 = 0;
+    { TcParams q = p; q.m_tiles = mh; q.row0 = 0;
+      if (c3.aux) { q.aux_cols = st->aux_h; q.aux_row0 = 0; }
       q.stages = c3.stages; q.lo_stages = c3.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 512;
       if (st->x3) launch_on<TC_BWD, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem);
       else launch_on<TC_BWD, false>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem); }
@@ -963,7 +977,7 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
     auto* st = static_cast<TcState*>(e.tc);
     StepPlan pl;
     pl.s0 = 0; pl.ns = e.S; pl.main = e.stream;
-    if (const char* v = getenv("DEEPIMPUTE_B200_DEEP")) pl.deep = atoi(v) != 0;
+    if (const char* v = getenv("DEEPIMPUTE_B200_DEEP")) pl.deep = std::max(0, std::min(2, atoi(v)));
     launch_step(e, st, a, which_x, pl);
     if (st->d_trace && which_x == 1) {          // explicit-batch step: dump the pipeline trace of CTA (0,0,0)
         static unsigned long long h[5 * 256];

@@ -16,6 +16,7 @@ for v in "$@"; do
   case $v in
     nograph) run nograph DEEPIMPUTE_B200_GRAPH=0 ;;
     g*_deep) g=${v#g}; g=${g%_deep}; run $v DEEPIMPUTE_B200_GROUPS=$g DEEPIMPUTE_B200_DEEP=1 ;;
+    g*_medium) g=${v#g}; g=${g%_medium}; run $v DEEPIMPUTE_B200_GROUPS=$g DEEPIMPUTE_B200_DEEP=2 ;;
     g*_shallow) g=${v#g}; g=${g%_shallow}; run $v DEEPIMPUTE_B200_GROUPS=$g DEEPIMPUTE_B200_DEEP=0 ;;
   esac
 done
