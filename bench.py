@@ -104,12 +104,19 @@ def build_workload(name, device):
     del corr
     norm = torch.empty((N, G), dtype=torch.float32, pin_memory=(dev.type == "cuda"))
     norm.copy_(torch.log1p(raw))
-    del raw, Z, W
+    raw_keep = raw
+    del Z, W
     if dev.type == "cuda":
         torch.cuda.empty_cache()
     np.random.seed(MODEL_SEED)
     train_rows, test_rows = partition.split_cells(N)
-    return dict(name=name, N=N, G=G, B=w["batch"], norm=norm, pred_idx=pred_idx,
+    raw_host = None
+    if os.environ.get("DI_BENCH_PREDICTORS", "1") != "0" and dev.type == "cuda":
+        raw_host = torch.empty((N, G), dtype=torch.float32, pin_memory=True)
+        raw_host.copy_(raw_keep)
+    del raw_keep, raw
+    cand_np = torch.nonzero(cand).reshape(-1).cpu().numpy().astype(np.int32)
+    return dict(name=name, N=N, G=G, B=w["batch"], norm=norm, pred_idx=pred_idx, raw=raw_host, cand=cand_np,
                 targ_idx=np.ascontiguousarray(targets, dtype=np.int32), train_rows=train_rows, test_rows=test_rows,
                 desc=w["desc"])
 
@@ -462,6 +469,23 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline,
         }
+        if world == 1 and wl.get("raw") is not None:
+            # SURVEY.md 8f row 1, outside every timed region above: correlation + top-5 predictor selection of the
+            # same matrix through di_corr_topk (host buffers in, indices out), checked against the set-up's selection
+            from deepimpute_b200 import partition as _part
+            t0 = time.perf_counter()
+            labels = np.array(["g{:06d}".format(j) for j in wl["cand"]], dtype=object)
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):          # the helper prints one line per sub-network
+                picked, dev_ms = _part.choose_predictors_gpu(wl["raw"].numpy(), wl["targ_idx"], wl["cand"], labels, 5,
+                                                             device=local)
+            secs = time.perf_counter() - t0
+            same = sum(len(np.intersect1d(a, b)) for a, b in zip(picked, wl["pred_idx"])) / float(sum(n_pred_all))
+            line["predictor_selection"] = {
+                "seconds": round(secs, 3), "device_ms": round(dev_ms, 1),
+                "TFLOP/s": round(2.0 * G * G * N / (dev_ms * 1e-3) / 1e12, 2),
+                "overlap_with_setup_selection": round(same, 5),
+                "note": "|corrcoef| of raw counts + per-target top-5 (multinet.py:20-34, :344-365); fp32 CUDA-core Gram kernel"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference(wl, args.epochs).items()
                                     if k not in ("t_fit_s", "t_predict_s", "sampled_s")}

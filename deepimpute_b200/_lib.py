@@ -41,6 +41,9 @@ SIGNATURES = {
     "di_validation_loss": (C.c_int, [_H, _f32p]),
     "di_predict": (C.c_int, [_H, _i32p, C.c_int64, _f32p]),
     "di_predict_device": (C.c_int, [_H, _i32p, C.c_int64, C.c_void_p, C.c_int64]),
+    "di_corr_topk": (C.c_int, [C.c_int32, _f32p, C.c_int64, C.c_int64, _i32p, C.c_int64, _i32p, C.c_int32, C.c_int32,
+                               C.c_int32, _i32p, _f32p, _f32p]),
+    "di_corr_last_error": (C.c_char_p, []),
     "di_device_sync": (C.c_int, [_H]),
     "di_timer_start": (C.c_int, [_H]),
     "di_timer_stop": (C.c_int, [_H, _f32p]),

@@ -87,6 +87,7 @@ class MultiNet:
                  math_mode=None,
                  device=None,
                  shard=None,
+                 predictor_engine="auto",
                  ):
         self.NN_parameters = {"learning_rate": learning_rate,
                               "batch_size": batch_size,
@@ -103,6 +104,10 @@ class MultiNet:
         self.math_mode = math_mode
         self.shard = shard
         self.device = device if device is not None else (shard.device if shard is not None else None)
+        if predictor_engine not in ("auto", "host", "gpu"):
+            raise ValueError("predictor_engine must be 'auto', 'host' or 'gpu'")
+        self.predictor_engine = predictor_engine
+        self.timings = {}
         self.engine = None
         self.history = None
         self._owned = None            # sub-networks of every rank (parallel.assign_subnets); None = unsharded
@@ -251,8 +256,20 @@ class MultiNet:
 
         raw_values = raw.values
         cand = partition.candidate_predictors(raw, n_pred)
-        corr = partition.abs_correlation(raw_values, cand)
-        self._set_partition(cols, raw_values, genes, cand, corr, ntop, mode)
+        # the correlation matrix is O(G^2 N): float64 numpy on the host for small inputs (bit-for-bit the reference's
+        # selection), the GPU (fp32, di_corr_topk) for large ones, where the host takes minutes
+        use_gpu = self.predictor_engine == "gpu" or (
+            self.predictor_engine == "auto" and n_pred is None and
+            float(len(cand)) ** 2 * raw.shape[0] >= 2e11)
+        import time as _time
+        t0 = _time.perf_counter()
+        if use_gpu:
+            self._set_partition_gpu(cols, raw_values, genes, cand, ntop, mode)
+        else:
+            corr = partition.abs_correlation(raw_values, cand)
+            self._set_partition(cols, raw_values, genes, cand, corr, ntop, mode)
+        self.timings["predictor_selection_s"] = _time.perf_counter() - t0
+        self.timings["predictor_engine"] = "gpu" if use_gpu else "host"
 
         print("Normalization")
         norm_values = np.ascontiguousarray(np.log1p(raw_values), dtype=np.float32)
@@ -314,6 +331,15 @@ class MultiNet:
             return partition.abs_correlation(raw_values, t, cand)
 
         pred_pos = partition.choose_predictors(targ_pos, cand, _labels(cols)[cand], corr_rows, ntop)
+        self.targets = _labels(cols)[targ_pos]
+        self.predictors = [cols[p] for p in pred_pos]
+
+    def _set_partition_gpu(self, cols, raw_values, genes, cand, ntop, mode):
+        """Same as ``_set_partition`` with correlations and top-``ntop`` scans on the GPU (``di_corr_topk``)."""
+        targ_pos = partition.assign_targets(genes, self.sub_outputdim, mode)
+        pred_pos, ms = partition.choose_predictors_gpu(raw_values, targ_pos, cand, _labels(cols)[cand], ntop,
+                                                       device=self.device if self.device is not None else 0)
+        self.timings["predictor_selection_device_ms"] = ms
         self.targets = _labels(cols)[targ_pos]
         self.predictors = [cols[p] for p in pred_pos]
 

@@ -106,6 +106,19 @@ int di_validation_loss(di_handle* h, float* val_loss_out);
 int di_predict(di_handle* h, const int32_t* rows, int64_t n, float* out);
 int di_predict_device(di_handle* h, const int32_t* rows, int64_t n, float* d_out, int64_t ld_out);
 
+/* Predictor selection (the O(G^2 N) step of fit).  |Pearson r| between genes on RAW
+ * counts raw[n_cells][n_genes] -- get_distance_matrix, multinet.py:20-34: abs(np.corrcoef(raw.T)), NaN -> 0 -- and for
+ * every target gene targ[s][o] the ntop (<= 8) most correlated candidates that are not targets of sub-network s --
+ * setPredictors, multinet.py:349-360: argsort(-|r|)[:, :ntop].  cand lists the candidate gene columns in the order
+ * ties are broken (the reference visits them label-sorted); top_out[s][o][k] is a POSITION into cand (or -1 when
+ * fewer than ntop candidates remain), val_out (optional) the |r| found.  Stand-alone: needs no handle, allocates and
+ * frees its own device memory on `device`; device_ms_out (optional) receives the CUDA-event time of the kernels.
+ * fp32 on the device against float64 in the reference: selections differ only at ties closer than ~1e-6. */
+int di_corr_topk(int32_t device, const float* raw, int64_t n_cells, int64_t n_genes, const int32_t* cand, int64_t n_cand,
+                 const int32_t* targ, int32_t n_subnets, int32_t sub_outputdim, int32_t ntop, int32_t* top_out,
+                 float* val_out, float* device_ms_out);
+const char* di_corr_last_error(void);
+
 /* Introspection for tests and benchmarks. */
 int di_device_sync(di_handle* h);
 /* CUDA-event stopwatch on the handle's own stream (the stream every kernel of this handle is launched on):
