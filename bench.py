@@ -174,6 +174,8 @@ def kernel_work(n_pred, B):
         "adam2": dict(bytes=24 * S * H * O + 4 * B * S * (H + O), flops=2 * B * S * H * O),
         "adam1": dict(bytes=24 * sumP * H + 4 * B * (sumP + S * H), flops=2 * B * sumP * H),
         "bias": dict(bytes=24 * S * (H + O) + 4 * B * S * (H + O), flops=B * S * (H + O)),
+        # tensor-core path: both weight matrices in one launch
+        "adam": dict(bytes=24 * (sumP * H + S * H * O) + 4 * B * (sumP + 2 * S * H + S * O), flops=2 * B * (sumP * H + S * H * O)),
     }
 
 
@@ -200,9 +202,10 @@ def load_traffic(workload, kernel, n_pred):
         return None
     S, cd = len(n_pred), lambda a, b: -(-a // b)
     max_pp = max(cd(p, 32) * 32 for p in n_pred)
-    grids = {"adam2": (cd(HIDDEN, 128), cd(OUT, 128), S), "adam1": (cd(max_pp, 128), cd(HIDDEN, 128), S),
+    grids = {"adam": (cd(max_pp, 128) + cd(HIDDEN, 128), max(cd(OUT, 128), cd(HIDDEN, 128)), S),
+             "adam2": (cd(HIDDEN, 128), cd(OUT, 128), S), "adam1": (cd(max_pp, 128), cd(HIDDEN, 128), S),
              "fwd1": (1, cd(HIDDEN, 128), S), "fwd2": (1, cd(OUT, 128), S), "bwd": (1, cd(HIDDEN, 128), S)}
-    names = {"adam2": "tc_adam_kernel", "adam1": "tc_adam_kernel", "fwd1": "tc_kernel<0", "fwd2": "tc_kernel<1",
+    names = {"adam": "tc_adam_kernel", "adam2": "tc_adam_kernel", "adam1": "tc_adam_kernel", "fwd1": "tc_kernel<0", "fwd2": "tc_kernel<1",
              "bwd": "tc_kernel<2"}
     if kernel not in grids:
         return None
@@ -408,7 +411,7 @@ def main():
     # ---- per-kernel timing of one more epoch (CUDA events around every launch on the engine's stream)
     eng.set_profiling(True)
     eng.train_epoch(epoch_permutation(MODEL_SEED, state["epoch"], n_train))
-    names = ["gather", "fwd1", "fwd2", "bwd", "adam2", "adam1", "bias", "infer1", "infer2"]
+    names = ["gather", "fwd1", "fwd2", "bwd", "adam", "adam2", "adam1", "bias", "infer1", "infer2"]
     kern = {k: (eng.kernel_ms(k), eng.kernel_launches(k)) for k in names if eng.kernel_launches(k) > 0}
     eng.set_profiling(False)
     epoch_ms = eng.last_device_ms()

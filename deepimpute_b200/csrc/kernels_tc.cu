@@ -64,7 +64,9 @@ struct TcParams {
     int m_tiles;                // feature tiles per sub-network
     int aux_cols;               // > 0: the epilogue's side operand (Y tile / h tile) is staged by TMA, row pitch in floats
     int64_t aux_row0;
-    int wbox;                   // ADAM: features per weight-tile row in shared memory (min(128, out_dim))
+    int wbox;                   // ADAM: features per weight-tile row in shared memory (min(128, out_dim)), W1 tiles
+    int wbox2;                  // ... W2 tiles
+    int nx1;                    // ADAM: blockIdx.x < nx1 -> W1 tiles (in = X, dout = dz1), else W2 tiles (in = h, dout = dz2)
     // epilogue operands
     const float* Y; int64_t ldy;                 // packed targets
     float* Hact; int64_t ldh;                    // [rows][S*Hp]
@@ -422,21 +424,23 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
 // X3: the error-compensated product needs dout_hi in_hi + dout_hi in_lo + dout_lo in_hi.  The residual twins already
 // exist in global memory (written by the kernels that produced dout / in), so the three terms are three
 // load -> MMA rounds through the SAME operand buffers: no second copy in shared memory, two CTAs per SM as before.
+// Both weight matrices are updated by ONE launch: blockIdx.x < nx1 are W1 tiles, the rest W2 tiles (fewer, larger
+// waves than two launches, and one kernel boundary less on the step's critical path).
+struct AdamMaps { CUtensorMap A, B, Alo, Blo, W, M, V; };   // dout, in, their residual twins, and the w / m / v tiles
+
 template <bool X3>
-__global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                              const __grid_constant__ CUtensorMap mapB,
-                                                              const __grid_constant__ CUtensorMap mapAlo,
-                                                              const __grid_constant__ CUtensorMap mapBlo,
-                                                              const __grid_constant__ CUtensorMap mapW,
-                                                              const __grid_constant__ CUtensorMap mapM,
-                                                              const __grid_constant__ CUtensorMap mapV, const TcParams p) {
+__global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_constant__ AdamMaps maps1,
+                                                              const __grid_constant__ AdamMaps maps2, const TcParams p) {
     const int s = blockIdx.z + p.s_base;
     const SubnetDesc d = p.desc[s];
+    const bool second = (int)blockIdx.x >= p.nx1;
+    const AdamMaps* mp = second ? &maps2 : &maps1;
+    const CUtensorMap &mapA = mp->A, &mapB = mp->B, &mapAlo = mp->Alo, &mapBlo = mp->Blo, &mapW = mp->W, &mapM = mp->M, &mapV = mp->V;
     const int m0 = blockIdx.y * TILE_M;
-    const int n0 = blockIdx.x * p.n_cols;
+    const int n0 = ((int)blockIdx.x - (second ? p.nx1 : 0)) * p.n_cols;
     int out_dim, in_dim, a_c0, b_c0, b_c1;
     int64_t row_base;                                     // first weight row of this sub-network
-    if (p.which == 1) { out_dim = p.Hp; in_dim = d.Pp; a_c0 = s * p.Hp + m0; b_c0 = (int)d.coff + n0; b_c1 = (int)p.row0; row_base = d.coff; }
+    if (!second) { out_dim = p.Hp; in_dim = d.Pp; a_c0 = s * p.Hp + m0; b_c0 = (int)d.coff + n0; b_c1 = (int)p.row0; row_base = d.coff; }
     else { out_dim = p.Op; in_dim = p.Hp; a_c0 = s * p.Op + m0; b_c0 = s * p.Hp + n0; b_c1 = 0; row_base = (int64_t)s * p.Hp; }
     if (m0 >= out_dim || n0 >= in_dim) return;
     const int nkb = p.nkb_adam;
@@ -449,7 +453,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)nkb * A_STAGE_BYTES;
     float* wring = reinterpret_cast<float*>(sB + (size_t)nkb * b_block_bytes);
-    const int wbox = p.wbox;
+    const int wbox = second ? p.wbox2 : p.wbox;
     const int tile_floats = AD_R * wbox;                  // one tensor, one chunk
     const uint32_t chunk_bytes = 3u * tile_floats * 4u;
     // ring stages: AD_STAGES dedicated ones, then as many as fit in the operand buffers, which are dead once the
@@ -876,9 +880,6 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     const TcState::Cfg& c2 = st->fwd2_train[pl.deep];
     const TcState::Cfg& c3 = st->bwd_train[pl.deep];
 
-    // the previous step's ADAM2 (side stream) still reads h and dz2, which FWD1 / FWD2 are about to overwrite, and
-    // writes W2, which FWD2 reads: the new step starts when it is done (ADAM2 therefore overlaps ADAM1 only)
-    if (pl.side && !pl.first) cudaStreamWaitEvent(pl.main, pl.ev_adam2, 0);
     { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
       q.stages = c1.stages; q.lo_stages = c1.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace;
       if (st->x3) launch_on<TC_FWD1, true>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem);
@@ -896,28 +897,23 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     if (st->simt_adam && !pl.graph) { simt_adam_only(e, a); return; }
     TcParams q = p;
     q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;
-    const CUtensorMap& Xlo = which_x == 0 ? st->Xtr_lo_mn : st->Xstep_lo_mn;
-    cudaStream_t s2 = pl.side ? pl.side : pl.main;
-    if (pl.side) { cudaEventRecord(pl.ev_bwd, pl.main); cudaStreamWaitEvent(pl.side, pl.ev_bwd, 0); }
-    { q.which = 2; q.row0 = 0; q.wbox = st->wbox2; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 768;
-      const dim3 grid(cdiv(e.Hp, ADAM_TILE), mo, pl.ns);
-      KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam2");
-      if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, s2>>>(
-          st->DZ2_mn, st->H_mn, st->DZ2lo_mn, st->Hlo_mn, st->W2_t[0], st->W2_t[1], st->W2_t[2], q);
-      else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, s2>>>(
-          st->DZ2_mn, st->H_mn, st->DZ2_mn, st->H_mn, st->W2_t[0], st->W2_t[1], st->W2_t[2], q);
-      if (t) { delete t; count_launch(e, "adam2"); } }
-    if (pl.side) cudaEventRecord(pl.ev_adam2, pl.side);
-    { q.which = 1; q.row0 = a.row0; q.wbox = st->wbox1; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 1024;
-      int maxPp = 0;
-      for (int s = pl.s0; s < pl.s0 + pl.ns; ++s) maxPp = std::max(maxPp, e.Pp[s]);
-      const dim3 grid(cdiv(maxPp, ADAM_TILE), mh, pl.ns);
-      KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam1");
-      if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, pl.main>>>(
-          st->DZ1_mn, Xmn, st->DZ1lo_mn, Xlo, st->W1_t[0], st->W1_t[1], st->W1_t[2], q);
-      else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, pl.main>>>(
-          st->DZ1_mn, Xmn, st->DZ1_mn, Xmn, st->W1_t[0], st->W1_t[1], st->W1_t[2], q);
-      if (t) { delete t; count_launch(e, "adam1"); } }
+    q.row0 = a.row0; q.wbox = st->wbox1; q.wbox2 = st->wbox2;
+    if (!pl.graph && st->d_trace) q.trace = st->d_trace + 768;
+    int maxPp = 0;
+    for (int s = pl.s0; s < pl.s0 + pl.ns; ++s) maxPp = std::max(maxPp, e.Pp[s]);
+    q.nx1 = cdiv(maxPp, ADAM_TILE);
+    const dim3 grid(q.nx1 + cdiv(e.Hp, ADAM_TILE), std::max(mh, mo), pl.ns);
+    AdamMaps m1, m2;
+    m1.A = st->DZ1_mn; m1.B = which_x == 0 ? st->Xtr_mn : st->Xstep_mn; m1.W = st->W1_t[0]; m1.M = st->W1_t[1]; m1.V = st->W1_t[2];
+    m2.A = st->DZ2_mn; m2.B = st->H_mn; m2.W = st->W2_t[0]; m2.M = st->W2_t[1]; m2.V = st->W2_t[2];
+    if (st->x3) {
+        m1.Alo = st->DZ1lo_mn; m1.Blo = which_x == 0 ? st->Xtr_lo_mn : st->Xstep_lo_mn;
+        m2.Alo = st->DZ2lo_mn; m2.Blo = st->Hlo_mn;
+    } else { m1.Alo = m1.A; m1.Blo = m1.B; m2.Alo = m2.A; m2.Blo = m2.B; }
+    KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam");
+    if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, pl.main>>>(m1, m2, q);
+    else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, pl.main>>>(m1, m2, q);
+    if (t) { delete t; count_launch(e, "adam"); }
 }
 
 // Capture one whole epoch -- every optimiser step of every sub-network group -- into a graph that is replayed with a
@@ -950,14 +946,12 @@ bool build_epoch_graph(Engine& e, TcState* st) {
         for (int g = 0; g < G; ++g) {
             StepPlan pl;
             pl.s0 = st->group_s0[g]; pl.ns = st->group_s0[g + 1] - st->group_s0[g];
-            pl.main = st->gstream[g][0]; pl.side = st->gstream[g][1];
-            pl.ev_bwd = st->gev[g][0]; pl.ev_adam2 = st->gev[g][1];
+            pl.main = st->gstream[g][0];
             pl.graph = true; pl.first = (i == 0); pl.deep = st->group_deep;
             launch_step(e, st, a, 0, pl);
         }
     }
     for (int g = 0; g < G; ++g) {
-        cudaStreamWaitEvent(st->gstream[g][0], st->gev[g][1], 0);      // join the side stream
         cudaEventRecord(st->gev[g][2], st->gstream[g][0]);
         cudaStreamWaitEvent(e.stream, st->gev[g][2], 0);
     }
@@ -966,7 +960,7 @@ bool build_epoch_graph(Engine& e, TcState* st) {
     ce = cudaGraphInstantiate(&st->epoch_exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { cudaGetLastError(); st->epoch_exec = nullptr; return false; }
-    st->graph_nodes = n_steps * G * 5;
+    st->graph_nodes = n_steps * G * 4;
     st->graph_n_train = e.n_train;
     return true;
 }
@@ -998,10 +992,10 @@ void tc_train_step(Engine& e, const StepArgs& a, int which_x) {
                 fprintf(stderr, "\n");
             }
         }
-        for (int k = 3; k < 5; ++k) {
+        for (int k = 3; k < 4; ++k) {
             const unsigned long long* t = h + 256 * k; const unsigned long long t0 = t[0];
             fprintf(stderr, "[trace %s] epilogue waits for accumulator from %llu | accumulator ready %llu | last chunk done %llu | exit %llu\n",
-                    k == 3 ? "adam2" : "adam1", t[2] - t0, t[3] - t0, t[4] - t0, t[5] - t0);
+                    "adam", t[2] - t0, t[3] - t0, t[4] - t0, t[5] - t0);
             fprintf(stderr, "   chunk: tile-in-smem  updated(store issued)\n");
             for (int c = 0; c < 40 && t[8 + c]; ++c)
                 fprintf(stderr, "   %2d: %9llu %9llu\n", c, t[8 + c] - t0, t[48 + c] ? t[48 + c] - t0 : 0ull);

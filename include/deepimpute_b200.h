@@ -132,7 +132,7 @@ int64_t di_launch_count(const di_handle* h);
 float di_last_device_ms(const di_handle* h);
 /* Average CUDA-event duration (ms) of the kernel named `which` over the last di_train_epoch, measured on the
  * handle's stream when profiling is enabled with di_set_profiling(h, 1); -1 if unknown.
- * names: "gather", "fwd1", "fwd2", "bwd", "adam2", "adam1", "bias" (training), "infer1", "infer2" (inference).
+ * names: "gather", "fwd1", "fwd2", "bwd", "adam" (tensor-core modes; "adam2", "adam1", "bias" in fp32 mode), "infer1", "infer2".
  * di_kernel_launches: how many launches of that kernel the average covers. */
 int di_set_profiling(di_handle* h, int32_t on);
 float di_kernel_ms(const di_handle* h, const char* which);
