@@ -10,6 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdeepimpute_b200.so")
 
 DI_MATH = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+DI_DTYPE = {"float32": 0, "float64": 1}
+DI_POLICY = {None: 0, "none": 0, "restore": 1, "max": 2}
 
 
 class DiConfig(C.Structure):
@@ -31,6 +33,7 @@ SIGNATURES = {
     "di_last_error": (C.c_char_p, [_H]),
     "di_set_subnet_ids": (C.c_int, [_H, _i32p]),
     "di_upload_matrix": (C.c_int, [_H, _f32p, C.c_int64, C.c_int64]),
+    "di_upload_counts": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int64, C.c_int64]),
     "di_set_partition": (C.c_int, [_H, _i32p, _i64p, _i32p]),
     "di_set_split": (C.c_int, [_H, _i32p, C.c_int64, _i32p, C.c_int64]),
     "di_set_weights": (C.c_int, [_H, C.c_int32, _f32p, _f32p, _f32p, _f32p]),
@@ -41,6 +44,7 @@ SIGNATURES = {
     "di_validation_loss": (C.c_int, [_H, _f32p]),
     "di_predict": (C.c_int, [_H, _i32p, C.c_int64, _f32p]),
     "di_predict_device": (C.c_int, [_H, _i32p, C.c_int64, C.c_void_p, C.c_int64]),
+    "di_impute": (C.c_int, [_H, C.c_int32, _i32p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "di_corr_topk": (C.c_int, [C.c_int32, _f32p, C.c_int64, C.c_int64, _i32p, C.c_int64, _i32p, C.c_int32, C.c_int32,
                                C.c_int32, _i32p, _f32p, _f32p]),
     "di_corr_last_error": (C.c_char_p, []),

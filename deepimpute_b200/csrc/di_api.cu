@@ -289,6 +289,9 @@ void di_destroy(di_handle* h) {
                      &e.Hlo, &e.DZ2lo, &e.DZ1lo, &e.Xstep_lo};
     for (float** p : all) dev_free(*p);
     dev_free(e.d_step_rows); dev_free(e.d_chunk_rows); dev_free(e.d_loss);
+    dev_free(e.d_raw_max); dev_free(e.d_gene_off); dev_free(e.d_gene_slots);
+    if (e.d_raw) cudaFree(e.d_raw);
+    for (int i = 0; i < 2; ++i) if (e.d_imp[i]) cudaFree(e.d_imp[i]);
     resolve_timers(e);
     for (cudaEvent_t ev : e.event_pool) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
@@ -317,11 +320,9 @@ int di_set_subnet_ids(di_handle* h, const int32_t* ids) {
     return sync_check(e);
 }
 
-int di_upload_matrix(di_handle* h, const float* norm, int64_t n_cells, int64_t n_genes) {
-    if (!h) return DI_ERR_ARG;
-    Engine& e = h->e;
-    if (!norm || n_cells <= 0 || n_genes <= 0) return fail(e, DI_ERR_ARG, "di_upload_matrix: bad arguments");
-    DI_CUDA(cudaSetDevice(e.cfg.device));
+// (re)allocates the resident normalised matrix for an n_cells x n_genes input; everything staged from the previous
+// matrix is dropped when the shape changes
+static int ensure_matrix(Engine& e, int64_t n_cells, int64_t n_genes) {
     if (n_cells != e.N || n_genes != e.G) {
         DI_CUDA(cudaStreamSynchronize(e.stream));
         dev_free(e.d_norm);
@@ -331,9 +332,58 @@ int di_upload_matrix(di_handle* h, const float* norm, int64_t n_cells, int64_t n
         if (rc) return rc;
         e.N = n_cells; e.G = n_genes;
     }
+    return DI_OK;
+}
+
+static void drop_counts(Engine& e) {
+    if (e.d_raw) cudaFree(e.d_raw);
+    e.d_raw = nullptr; e.raw_dtype = -1; e.raw_max = 0.0;
+}
+
+int di_upload_matrix(di_handle* h, const float* norm, int64_t n_cells, int64_t n_genes) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!norm || n_cells <= 0 || n_genes <= 0) return fail(e, DI_ERR_ARG, "di_upload_matrix: bad arguments");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    int rc = ensure_matrix(e, n_cells, n_genes);
+    if (rc) return rc;
+    DI_CUDA(cudaStreamSynchronize(e.stream));
+    drop_counts(e);                 // the counts of a previous di_upload_counts no longer describe this matrix
     DI_CUDA(cudaMemcpyAsync(e.d_norm, norm, (size_t)n_cells * n_genes * sizeof(float), cudaMemcpyHostToDevice, e.stream));
     e.split_stale = true;           // staged train / test matrices (if any) hold values of the previous matrix
     return sync_check(e);
+}
+
+int di_upload_counts(di_handle* h, const void* raw, int32_t dtype, int64_t n_cells, int64_t n_genes) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!raw || n_cells <= 0 || n_genes <= 0 || (dtype != DI_DTYPE_F32 && dtype != DI_DTYPE_F64))
+        return fail(e, DI_ERR_ARG, "di_upload_counts: bad arguments");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+    const bool same = e.d_raw && dtype == e.raw_dtype && n_cells == e.N && n_genes == e.G;
+    int rc = ensure_matrix(e, n_cells, n_genes);
+    if (rc) return rc;
+    const size_t bytes = (size_t)n_cells * n_genes * (dtype == DI_DTYPE_F64 ? sizeof(double) : sizeof(float));
+    if (!same) {
+        DI_CUDA(cudaStreamSynchronize(e.stream));
+        drop_counts(e);
+        DI_CUDA(cudaMalloc(&e.d_raw, bytes));
+        e.raw_dtype = dtype;
+    }
+    if (!e.d_raw_max && (rc = dev_alloc(e, &e.d_raw_max, 1))) return rc;
+    DI_CUDA(cudaMemcpyAsync(e.d_raw, raw, bytes, cudaMemcpyHostToDevice, e.stream));
+    DI_CUDA(cudaMemsetAsync(e.d_raw_max, 0, sizeof(unsigned long long), e.stream));
+    DI_CUDA(cudaEventRecord(e.ev0, e.stream));
+    launch_counts_to_norm(e, e.d_raw, dtype, e.d_norm, n_cells * n_genes, e.d_raw_max);
+    DI_CUDA(cudaEventRecord(e.ev1, e.stream));
+    unsigned long long bits = 0;
+    DI_CUDA(cudaMemcpyAsync(&bits, e.d_raw_max, sizeof bits, cudaMemcpyDeviceToHost, e.stream));
+    e.split_stale = true;
+    rc = sync_check(e);
+    if (rc) return rc;
+    memcpy(&e.raw_max, &bits, sizeof bits);
+    DI_CUDA(cudaEventElapsedTime(&e.last_ms, e.ev0, e.ev1));
+    return DI_OK;
 }
 
 int di_set_partition(di_handle* h, const int32_t* pred_idx, const int64_t* pred_off, const int32_t* targ_idx) {
@@ -360,6 +410,7 @@ int di_set_partition(di_handle* h, const int32_t* pred_idx, const int64_t* pred_
     DI_CUDA(cudaMemcpyAsync(e.d_targ_cols, tc.data(), tc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
     int rc = sync_check(e);
     e.have_partition = rc == DI_OK;
+    e.h_targ.assign(targ_idx, targ_idx + (size_t)e.S * e.O);
     // a new partition invalidates the CONTENTS of the staged train/test matrices; the buffers (and everything bound
     // to their addresses: tensor maps, the epoch graph) are kept and refilled by the next di_set_split
     e.split_stale = true;
@@ -613,6 +664,92 @@ int di_predict_device(di_handle* h, const int32_t* rows, int64_t n, float* d_out
     return predict_impl(h, rows, n, nullptr, d_out, ld_out);
 }
 
+int di_impute(di_handle* h, int32_t policy, const int32_t* slot_gene, int64_t n_slots, const float* d_pred,
+              int64_t ld_pred, int32_t out_dtype, void* out) {
+    if (!h) return DI_ERR_ARG;
+    Engine& e = h->e;
+    if (!e.d_raw) return fail(e, DI_ERR_ARG, "di_impute: no counts on the device (di_upload_counts)");
+    if (!out || (out_dtype != DI_DTYPE_F32 && out_dtype != DI_DTYPE_F64) ||
+        (policy != DI_POLICY_NONE && policy != DI_POLICY_RESTORE && policy != DI_POLICY_MAX))
+        return fail(e, DI_ERR_ARG, "di_impute: bad arguments");
+    const int64_t SO = (int64_t)e.S * e.O;
+    if (!d_pred) {
+        if (!e.have_partition) return fail(e, DI_ERR_ARG, "di_impute: no partition (di_set_partition)");
+        if (slot_gene && n_slots != SO) return fail(e, DI_ERR_ARG, "di_impute: n_slots must be S*O when the handle predicts");
+        ld_pred = SO;
+    } else if (!slot_gene || ld_pred < n_slots) {
+        return fail(e, DI_ERR_ARG, "di_impute: a prediction matrix needs its slot table and ld_pred >= n_slots");
+    }
+    if (!slot_gene) {
+        if (!e.have_partition) return fail(e, DI_ERR_ARG, "di_impute: no partition (di_set_partition)");
+        slot_gene = e.h_targ.data(); n_slots = SO;
+    }
+    if (n_slots < 0) return fail(e, DI_ERR_ARG, "di_impute: negative n_slots");
+    DI_CUDA(cudaSetDevice(e.cfg.device));
+
+    // gene -> prediction columns (CSR, columns ascending inside a gene); a negative slot_gene entry is ignored
+    std::vector<int32_t> ent((size_t)2 * e.G, 0), slots((size_t)std::max<int64_t>(n_slots, 1));
+    for (int64_t k = 0; k < n_slots; ++k) {
+        if (slot_gene[k] >= e.G) return fail(e, DI_ERR_ARG, "di_impute: slot gene out of range");
+        if (slot_gene[k] >= 0) ++ent[2 * (size_t)slot_gene[k] + 1];
+    }
+    int32_t run = 0;
+    for (int64_t g = 0; g < e.G; ++g) { ent[2 * g] = run; run += ent[2 * g + 1]; ent[2 * g + 1] = 0; }
+    for (int64_t k = 0; k < n_slots; ++k) {
+        if (slot_gene[k] < 0) continue;
+        const size_t g = (size_t)slot_gene[k];
+        slots[(size_t)ent[2 * g] + ent[2 * g + 1]++] = (int32_t)k;
+    }
+    int rc;
+    DI_CUDA(cudaStreamSynchronize(e.stream));
+    dev_free(e.d_gene_off); dev_free(e.d_gene_slots);
+    if ((rc = dev_alloc(e, &e.d_gene_off, 2 * e.G, false))) return rc;
+    if ((rc = dev_alloc(e, &e.d_gene_slots, (int64_t)slots.size(), false))) return rc;
+    DI_CUDA(cudaMemcpyAsync(e.d_gene_off, ent.data(), ent.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
+    DI_CUDA(cudaMemcpyAsync(e.d_gene_slots, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
+
+    const size_t esz = out_dtype == DI_DTYPE_F64 ? sizeof(double) : sizeof(float);
+    const int64_t rows_max = std::min<int64_t>(e.chunk_rows, round_up64(e.N, 128));
+    const size_t need = (size_t)rows_max * e.G * esz;
+    if (e.imp_bytes < need) {
+        for (int i = 0; i < 2; ++i) { if (e.d_imp[i]) cudaFree(e.d_imp[i]); e.d_imp[i] = nullptr; }
+        e.imp_bytes = 0;
+        for (int i = 0; i < 2; ++i) DI_CUDA(cudaMalloc(&e.d_imp[i], need));
+        e.imp_bytes = need;
+    }
+    const double clamp = 2.0 * std::log1p(e.raw_max);     // 2 * norm.max() of multinet.py:291, float64 like numpy
+
+    DI_CUDA(cudaEventRecord(e.ev0, e.stream));
+    int buf = 0;
+    for (int64_t r0 = 0; r0 < e.N; r0 += e.chunk_rows, buf ^= 1) {
+        const int64_t valid = std::min(e.chunk_rows, e.N - r0);
+        // the copy of chunk i-2 out of this buffer pair must have finished before chunk i overwrites it
+        DI_CUDA(cudaStreamWaitEvent(e.stream, e.ev_pinned[buf], 0));
+        const float* pred;
+        if (d_pred) {
+            pred = d_pred + r0 * ld_pred;
+        } else {
+            const int64_t rows_pad = round_up64(valid, 128);
+            launch_gather(e, nullptr, nullptr, r0, rows_pad, valid, e.d_pred_cols, e.PT, e.Xchunk);
+            run_forward(e, 3, e.Xchunk, nullptr, 0, rows_pad, valid, e.Ochunk2[buf], SO);
+            pred = e.Ochunk2[buf];
+        }
+        launch_impute(e, pred, ld_pred, r0, valid, clamp, policy, out_dtype, e.d_imp[buf]);
+        DI_CUDA(cudaEventRecord(e.ev_fwd[buf], e.stream));
+        DI_CUDA(cudaStreamWaitEvent(e.copy_stream, e.ev_fwd[buf], 0));
+        DI_CUDA(cudaMemcpyAsync(static_cast<char*>(out) + (size_t)r0 * e.G * esz, e.d_imp[buf], (size_t)valid * e.G * esz,
+                                cudaMemcpyDefault, e.copy_stream));
+        DI_CUDA(cudaEventRecord(e.ev_pinned[buf], e.copy_stream));
+    }
+    DI_CUDA(cudaStreamWaitEvent(e.stream, e.ev_pinned[0], 0));
+    DI_CUDA(cudaStreamWaitEvent(e.stream, e.ev_pinned[1], 0));
+    DI_CUDA(cudaEventRecord(e.ev1, e.stream));
+    rc = sync_check(e);
+    if (rc) return rc;
+    DI_CUDA(cudaEventElapsedTime(&e.last_ms, e.ev0, e.ev1));
+    return DI_OK;
+}
+
 int di_device_sync(di_handle* h) {
     if (!h) return DI_ERR_ARG;
     Engine& e = h->e;
@@ -665,14 +802,15 @@ int64_t di_kernel_launches(const di_handle* h, const char* which) {
 int di_debug_read(di_handle* h, const char* which, float* out, int64_t capacity_floats, int64_t* ld) {
     if (!h || !which || !out || !ld) return DI_ERR_ARG;
     Engine& e = h->e;
-    const float* src; int64_t pitch;
+    const float* src; int64_t pitch, rows = e.Bp;
     if (!strcmp(which, "h")) { src = e.Hact; pitch = (int64_t)e.S * e.Hp; }
     else if (!strcmp(which, "dz2")) { src = e.DZ2; pitch = (int64_t)e.S * e.Op; }
     else if (!strcmp(which, "dz1")) { src = e.DZ1; pitch = (int64_t)e.S * e.Hp; }
+    else if (!strcmp(which, "norm")) { src = e.d_norm; pitch = e.G; rows = e.N; }   // the resident normalised matrix
     else return fail(e, DI_ERR_ARG, "di_debug_read: unknown buffer");
-    if (capacity_floats < pitch * e.Bp) return fail(e, DI_ERR_ARG, "di_debug_read: buffer too small");
+    if (!src || capacity_floats < pitch * rows) return fail(e, DI_ERR_ARG, "di_debug_read: buffer too small");
     DI_CUDA(cudaSetDevice(e.cfg.device));
-    DI_CUDA(cudaMemcpyAsync(out, src, (size_t)pitch * e.Bp * sizeof(float), cudaMemcpyDeviceToHost, e.stream));
+    DI_CUDA(cudaMemcpyAsync(out, src, (size_t)pitch * rows * sizeof(float), cudaMemcpyDeviceToHost, e.stream));
     *ld = pitch;
     return sync_check(e);
 }

@@ -46,6 +46,15 @@ struct Engine {
     int32_t* d_pred_cols = nullptr; // [PT]   gene column of every packed X column, -1 = padding
     int32_t* d_targ_cols = nullptr; // [S*Op] gene column of every packed Y column, -1 = padding
     bool have_partition = false;
+    std::vector<int32_t> h_targ;    // host copy of the target columns [S*O] (slot -> gene table of di_impute)
+    // raw counts as uploaded by di_upload_counts (fp32 or fp64), kept for the restore / max policies of di_impute
+    void* d_raw = nullptr;
+    int raw_dtype = -1;             // DI_DTYPE_F32 / DI_DTYPE_F64, -1 = the matrix came through di_upload_matrix
+    double raw_max = 0.0;           // largest count of the matrix (the clamp of multinet.py:291 is 2*log1p of it)
+    unsigned long long* d_raw_max = nullptr;
+    int32_t *d_gene_off = nullptr, *d_gene_slots = nullptr;   // CSR gene -> prediction columns (di_impute)
+    void* d_imp[2] = {nullptr, nullptr};                      // [imp_rows][G] imputed chunk, double-buffered
+    int64_t imp_rows = 0; size_t imp_bytes = 0;
     bool split_stale = false;       // partition changed since di_set_split: staged matrices must be refilled
 
     float *W1 = nullptr, *mW1 = nullptr, *vW1 = nullptr;
@@ -106,6 +115,16 @@ void launch_gather(Engine& e, const int32_t* rows, const int32_t* perm, int64_t 
 // TF32 residual twin when X_lo != nullptr), Y -> [n_out][S*Op].  Row mapping as in launch_gather.
 void launch_gather_xy(Engine& e, const int32_t* rows, const int32_t* perm, int64_t n_out, int64_t n_valid,
                       int batch, int batch_pitch, float* X, float* X_lo, float* Y);
+
+// ---- counts -> log1p and the fused tail of predict (impute.cu) -----------------------------------------------
+// norm[i] = (float)log1p((double)raw[i]) for n values (multinet.py:217, :271) and *max_bits = bits of the largest
+// non-negative count as a double (atomicMax on the ordered bit pattern); dtype = DI_DTYPE_*
+void launch_counts_to_norm(Engine& e, const void* raw, int dtype, float* norm, int64_t n, unsigned long long* max_bits);
+// out[r][g] for r in [0, rows), g in [0, G): the imputed count of multinet.py:282-303 (duplicate-slot mean, overflow
+// clamp, expm1, restore / max policy).  pred: [rows][ld_pred] predictions of these rows; raw: first of the rows in
+// the resident count matrix; out_dtype = DI_DTYPE_*
+void launch_impute(Engine& e, const float* pred, int64_t ld_pred, int64_t row0, int64_t rows, double clamp,
+                   int policy, int out_dtype, void* out);
 
 // ---- fp32 CUDA-core path (kernels_simt.cu) -------------------------------------------------------------------
 void simt_train_step(Engine& e, const StepArgs& a);

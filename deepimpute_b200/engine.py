@@ -82,7 +82,8 @@ class Engine:
         if subnet_ids is not None:
             ids = np.asarray(self.subnet_ids, dtype=np.int32)
             self._check(self.lib.di_set_subnet_ids(self._h, _lib.i32(ids)))
-        self.n_cells = None
+        self.n_cells = self.n_genes = None
+        self.has_counts = False
         self.n_train = self.n_test = 0
         self.steps_done = 0
         if init_weights:
@@ -106,11 +107,7 @@ class Engine:
             pass
 
     # -- data -----------------------------------------------------------------------------------------------
-    def set_data(self, norm, pred_idx, targ_idx):
-        """norm [N, G] float32 (log1p of counts); pred_idx: S int arrays of gene columns; targ_idx [S, O]."""
-        norm = np.ascontiguousarray(norm, dtype=np.float32)
-        if norm.ndim != 2:
-            raise ValueError("norm must be 2-D")
+    def _check_partition(self, n_genes, pred_idx, targ_idx):
         if len(pred_idx) != self.S or [len(p) for p in pred_idx] != self.n_pred:
             raise ValueError("pred_idx does not match the engine's input dims")
         targ_idx = np.ascontiguousarray(targ_idx, dtype=np.int32)
@@ -119,11 +116,37 @@ class Engine:
         flat = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32) for p in pred_idx]))
         off = np.concatenate([[0], np.cumsum(self.n_pred)]).astype(np.int64)
         for name, idx in (("pred_idx", flat), ("targ_idx", targ_idx)):
-            if idx.size and (idx.min() < 0 or idx.max() >= norm.shape[1]):
-                raise ValueError("{} out of range for a matrix with {} genes".format(name, norm.shape[1]))
+            if idx.size and (idx.min() < 0 or idx.max() >= n_genes):
+                raise ValueError("{} out of range for a matrix with {} genes".format(name, n_genes))
+        return flat, off, targ_idx
+
+    def set_data(self, norm, pred_idx, targ_idx):
+        """norm [N, G] float32 (log1p of counts); pred_idx: S int arrays of gene columns; targ_idx [S, O]."""
+        norm = np.ascontiguousarray(norm, dtype=np.float32)
+        if norm.ndim != 2:
+            raise ValueError("norm must be 2-D")
+        flat, off, targ_idx = self._check_partition(norm.shape[1], pred_idx, targ_idx)
         self._check(self.lib.di_upload_matrix(self._h, _lib.f32(norm), norm.shape[0], norm.shape[1]))
         self._check(self.lib.di_set_partition(self._h, _lib.i32(flat), _lib.i64(off), _lib.i32(targ_idx)))
-        self.n_cells = norm.shape[0]
+        self.n_cells, self.n_genes = norm.shape
+        self.has_counts = False
+        self.n_train = self.n_test = 0
+
+    def set_counts(self, raw, pred_idx, targ_idx):
+        """Like ``set_data`` but from RAW counts [N, G] (float32 or float64): ``log1p`` -> float32 runs on the device
+        (multinet.py:217, :271) and the counts stay resident for ``impute``."""
+        raw = np.asarray(raw)
+        if raw.dtype != np.float32:
+            raw = raw.astype(np.float64, copy=False)
+        raw = np.ascontiguousarray(raw)
+        if raw.ndim != 2:
+            raise ValueError("raw must be 2-D")
+        flat, off, targ_idx = self._check_partition(raw.shape[1], pred_idx, targ_idx)
+        self._check(self.lib.di_upload_counts(self._h, C.c_void_p(raw.ctypes.data), _lib.DI_DTYPE[raw.dtype.name],
+                                              raw.shape[0], raw.shape[1]))
+        self._check(self.lib.di_set_partition(self._h, _lib.i32(flat), _lib.i64(off), _lib.i32(targ_idx)))
+        self.n_cells, self.n_genes = raw.shape
+        self.has_counts = True
         self.n_train = self.n_test = 0
 
     def set_split(self, train_rows, test_rows):
@@ -254,6 +277,41 @@ class Engine:
         self.predict_device(out.data_ptr(), self.S * self.O, rows)
         return out
 
+    def impute(self, policy="restore", out=None, dtype=np.float64, pred=None, slot_gene=None):
+        """The fused tail of ``MultiNet.predict`` (multinet.py:278-303) for all cells: forward, duplicate-target mean,
+        overflow clamp, ``expm1`` and the ``policy`` against the resident counts -> ``[N, G]`` array of ``dtype``.
+
+        ``pred``: optional torch CUDA tensor ``[N, n_slots]`` float32 of predictions made elsewhere (the all-gathered
+        blocks of a sharded model) with ``slot_gene[n_slots]`` naming the gene column each prediction column targets;
+        by default the engine predicts with its own sub-networks.  Needs ``set_counts``."""
+        if not self.has_counts:
+            raise RuntimeError("impute() needs the raw counts on the device: call set_counts() first")
+        if policy not in _lib.DI_POLICY:
+            policy = "none"          # the reference ignores unknown policies (multinet.py:295-302)
+        dtype = np.dtype(dtype)
+        if dtype.name not in _lib.DI_DTYPE:
+            raise ValueError("dtype must be float32 or float64")
+        if out is None:
+            out = np.empty((self.n_cells, self.n_genes), dtype=dtype)
+        if out.dtype != dtype or not out.flags.c_contiguous or out.shape != (self.n_cells, self.n_genes):
+            raise ValueError("out must be a C-contiguous [N, G] array of the requested dtype")
+        sg, n_slots, dp, ld = None, 0, None, 0
+        if slot_gene is not None:
+            slot_gene = np.ascontiguousarray(slot_gene, dtype=np.int32).reshape(-1)
+            sg, n_slots = _lib.i32(slot_gene), len(slot_gene)
+        if pred is not None:
+            if slot_gene is None:
+                raise ValueError("pred needs slot_gene")
+            if pred.dtype.__str__() != "torch.float32" or not pred.is_cuda or pred.dim() != 2 or \
+                    pred.shape[0] != self.n_cells or pred.shape[1] < n_slots or pred.stride(1) != 1:
+                raise ValueError("pred must be a float32 CUDA tensor [N, >= n_slots] with unit column stride")
+            import torch
+            torch.cuda.current_stream(pred.device).synchronize()
+            dp, ld = C.c_void_p(pred.data_ptr()), pred.stride(0)
+        self._check(self.lib.di_impute(self._h, _lib.DI_POLICY[policy], sg, n_slots, dp, ld,
+                                       _lib.DI_DTYPE[dtype.name], C.c_void_p(out.ctypes.data)))
+        return out
+
     # -- Keras-shaped adapters (lists of arrays, as the reference passes them) -----------------------------
     def _concat(self, X_list, Y_list=None):
         n = X_list[0].shape[0]
@@ -354,6 +412,13 @@ class Engine:
 
     def kernel_launches(self, which):
         return int(self.lib.di_kernel_launches(self._h, which.encode()))
+
+    def read_norm(self):
+        """The normalised matrix as it sits in HBM, [N, G] float32 (parity check of the device-side log1p)."""
+        buf = np.empty((self.n_cells, self.n_genes), np.float32)
+        ld = C.c_int64()
+        self._check(self.lib.di_debug_read(self._h, b"norm", _lib.f32(buf), buf.size, C.byref(ld)))
+        return buf
 
     def debug_read(self, which):
         ncols = self.S * (self.O if which == "dz2" else self.H) * 2 + 4096

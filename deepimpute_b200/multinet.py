@@ -66,7 +66,8 @@ class MultiNet:
     """Drop-in for ``deepimpute.multinet.MultiNet`` (reference ``multinet.py:65-375``).
 
     Extra keyword-only arguments (not in the reference): ``math_mode`` ("tf32x3" tensor-core kernels, default; "tf32"; or
-    "fp32" CUDA-core kernels), ``device`` (CUDA ordinal) and ``shard`` (a ``parallel.ShardContext``: this process
+    "fp32" CUDA-core kernels), ``postprocess`` ("gpu": fused device-side ``log1p`` / imputation tail, default; "host": numpy),
+    ``device`` (CUDA ordinal) and ``shard`` (a ``parallel.ShardContext``: this process
     trains only its share of the sub-networks and the per-epoch losses / predicted blocks are exchanged with the
     other ranks; see ``deepimpute_b200.parallel``).
     """
@@ -88,6 +89,7 @@ class MultiNet:
                  device=None,
                  shard=None,
                  predictor_engine="auto",
+                 postprocess="gpu",
                  ):
         self.NN_parameters = {"learning_rate": learning_rate,
                               "batch_size": batch_size,
@@ -107,6 +109,12 @@ class MultiNet:
         if predictor_engine not in ("auto", "host", "gpu"):
             raise ValueError("predictor_engine must be 'auto', 'host' or 'gpu'")
         self.predictor_engine = predictor_engine
+        if postprocess not in ("gpu", "host"):
+            raise ValueError("postprocess must be 'gpu' or 'host'")
+        # "gpu": log1p of the counts and the whole tail of predict (multinet.py:217, :271, :282-303) run on the device
+        # (di_upload_counts / di_impute); "host": the numpy restatement of those lines, which is also what an engine
+        # without the fused entry points (the CPU stand-in of the test-suite) is driven with
+        self.postprocess = postprocess
         self.timings = {}
         self.engine = None
         self.history = None
@@ -272,7 +280,9 @@ class MultiNet:
         self.timings["predictor_engine"] = "gpu" if use_gpu else "host"
 
         print("Normalization")
-        norm_values = np.ascontiguousarray(np.log1p(raw_values), dtype=np.float32)
+        on_device = self.postprocess == "gpu"
+        if not on_device:
+            norm_values = np.ascontiguousarray(np.log1p(raw_values), dtype=np.float32)
 
         np.random.seed(self.seed)
         train_rows, test_rows = partition.split_cells(raw.shape[0], labels=_labels(raw.index))
@@ -282,13 +292,16 @@ class MultiNet:
         model = self.build([len(p) for p in self.predictors])
 
         # The reference materialises 4*S pandas gathers here (multinet.py:231-235); the engine takes the
-        # normalised matrix once plus integer index tables and gathers on the device.
+        # matrix once plus integer index tables and gathers on the device.
         pred_idx = [cols.get_indexer(p).astype(np.int32) for p in self.predictors]
         targ_idx = cols.get_indexer(self.targets.reshape(-1)).reshape(self.targets.shape).astype(np.int32)
         mine = self._my_subnets(len(pred_idx))
 
         print("Fitting with {} cells".format(raw.shape[0]))
-        model.set_data(norm_values, [pred_idx[s] for s in mine], targ_idx[mine])
+        if on_device:       # raw counts go up once; log1p -> float32 (multinet.py:217) happens in HBM
+            model.set_counts(raw_values, [pred_idx[s] for s in mine], targ_idx[mine])
+        else:
+            model.set_data(norm_values, [pred_idx[s] for s in mine], targ_idx[mine])
         # Keras sums the per-branch losses and EarlyStopping watches the sum (multinet.py:242-243): when the
         # branches live on several GPUs the two scalars are summed over ranks before the stop decision
         exchange = None
@@ -307,7 +320,10 @@ class MultiNet:
         self.save(model)
 
         # held-out metrics on originally non-zero entries (multinet.py:251-262)
-        y_true = norm_values[np.ix_(test_rows, targ_idx.reshape(-1))].reshape(-1)
+        if on_device:       # only the held-out block is normalised on the host
+            y_true = np.log1p(raw_values[np.ix_(test_rows, targ_idx.reshape(-1))]).astype(np.float32).reshape(-1)
+        else:
+            y_true = norm_values[np.ix_(test_rows, targ_idx.reshape(-1))].reshape(-1)
         y_hat = self._predict_matrix(model, test_rows).reshape(-1)
         seen = y_true > 0
         y_true, y_hat = y_true[seen], y_hat[seen]
@@ -350,9 +366,6 @@ class MultiNet:
                 imputed_only=False,
                 policy="restore"):
 
-        norm_raw = np.log1p(raw)
-        norm_values = norm_raw.values
-
         model = self.engine if self.engine is not None else self.load()
 
         cols = raw.columns
@@ -364,22 +377,38 @@ class MultiNet:
             from .parallel import assign_subnets
             self._owned = assign_subnets([len(p) for p in pred_idx], self.shard.world_size, model.H, model.O)
         mine = self._my_subnets(len(pred_idx))
+
+        if self.postprocess == "gpu":
+            # fused path: counts up once, log1p + forward + duplicate mean + clamp + expm1 + policy on the device,
+            # one float64 [N, G] matrix back (multinet.py:271-303)
+            model.set_counts(raw.values, [pred_idx[s] for s in mine], targ_idx[mine])
+            if policy == "restore":
+                print("Filling zeros")
+            elif policy == "max":
+                print("Imputing data with 'max' policy")
+            if self._owned is None:
+                values = model.impute(policy=policy)
+            else:   # sharded: all-gather the prediction blocks on the devices, every rank finishes its own copy
+                full = self.shard.gather_blocks_device(model.predict_block(), self._owned, self.sub_outputdim)
+                values = model.impute(policy=policy, pred=full, slot_gene=targ_pos)
+            imputed = pd.DataFrame(values, index=raw.index, columns=raw.columns)
+            if imputed_only:
+                return imputed.loc[:, np.unique(targets_flat)]
+            return imputed
+
+        norm_raw = np.log1p(raw)
+        norm_values = norm_raw.values
         model.set_data(np.ascontiguousarray(norm_values, dtype=np.float32), [pred_idx[s] for s in mine],
                        targ_idx[mine])
 
         predicted = self._predict_matrix(model)           # [N, S*O] float32, columns = targets.flatten()
 
-        # mean over duplicated target columns (multinet.py:284), groups in sorted label order
-        uniq_labels, inverse, counts = np.unique(targets_flat, return_inverse=True, return_counts=True)
+        # mean over duplicated target columns (multinet.py:284): the reference's own pandas operation -- a column
+        # groupby-mean of a float32 frame -- spelled through a transpose because pandas 3 dropped groupby(axis=1)
+        uniq_labels = np.unique(targets_flat)
         uniq_pos = cols.get_indexer(uniq_labels)
-        if len(uniq_labels) == len(targets_flat):
-            pred_u = predicted[:, np.argsort(inverse, kind="stable")]
-        else:
-            acc = np.zeros((predicted.shape[0], len(uniq_labels)), dtype=np.float64)
-            order = np.argsort(inverse, kind="stable")
-            starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
-            acc[:] = np.add.reduceat(predicted[:, order].astype(np.float64), starts, axis=1)
-            pred_u = (acc / counts).astype(np.float32)
+        grouped = pd.DataFrame(predicted, columns=targets_flat).T.groupby(level=0).mean().T
+        pred_u = grouped.loc[:, uniq_labels].values
 
         imputed = np.array(norm_values, dtype=np.float64, copy=True)
         imputed[:, uniq_pos] = pred_u

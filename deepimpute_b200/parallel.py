@@ -93,6 +93,33 @@ class ShardContext:
                 out[:, s * width:(s + 1) * width] = host[r, :, k * width:(k + 1) * width]
         return out
 
+    def gather_blocks_device(self, block, owned, width):
+        """``gather_blocks`` that stays on the GPU: returns a float32 CUDA tensor ``[N, S * width]`` with the columns
+        in global sub-network order (input of the fused imputation tail, ``Engine.impute(pred=...)``)."""
+        import torch
+        if not self.distributed:
+            return block
+        if isinstance(block, np.ndarray):          # gloo runs of the test-suite hand in host arrays
+            block = torch.from_numpy(block)
+        n = block.shape[0]
+        counts = [len(o) for o in owned]
+        wmax = max(counts) * width
+        if block.shape[1] != counts[self.rank] * width:
+            raise ValueError("block has {} columns, expected {}".format(block.shape[1], counts[self.rank] * width))
+        if block.shape[1] == wmax:
+            padded = block.contiguous()
+        else:
+            padded = torch.zeros((n, wmax), dtype=torch.float32, device=block.device)
+            padded[:, :block.shape[1]] = block
+        full = torch.empty((self.world_size * n, wmax), dtype=torch.float32, device=block.device)
+        self._dist().all_gather_into_tensor(full, padded)
+        out = torch.empty((n, sum(counts) * width), dtype=torch.float32, device=block.device)
+        parts = full.view(self.world_size, n, wmax)
+        for r, subnets in enumerate(owned):
+            for k, s in enumerate(subnets):
+                out[:, s * width:(s + 1) * width] = parts[r, :, k * width:(k + 1) * width]
+        return out
+
     def barrier(self):
         if self.distributed:
             self._dist().barrier()

@@ -37,6 +37,13 @@ extern "C" {
 #define DI_MATH_TF32X3   2   /* same kernels, forward GEMMs error-compensated (a_hi b_hi + a_hi b_lo + a_lo b_hi):
                                 fp32-level activations and predictions; gradient GEMMs stay single-pass TF32 */
 
+#define DI_DTYPE_F32     0   /* element type of a count matrix / of the imputed output */
+#define DI_DTYPE_F64     1
+
+#define DI_POLICY_NONE     0 /* MultiNet.predict(policy=...) (multinet.py:295-302): keep the network's value        */
+#define DI_POLICY_RESTORE  1 /* "restore": observed counts > 0 are kept, only zeros are imputed (the default)        */
+#define DI_POLICY_MAX      2 /* "max": the larger of the observed count and the imputed one                          */
+
 typedef struct di_handle di_handle;
 
 /* Hyper-parameters fixed at build time.  Replaces MultiNet.build + model.compile(Adam(lr), wMSE)
@@ -72,6 +79,11 @@ int di_set_subnet_ids(di_handle* h, const int32_t* ids);
 int di_upload_matrix(di_handle* h, const float* norm, int64_t n_cells, int64_t n_genes);
 int di_set_partition(di_handle* h, const int32_t* pred_idx, const int64_t* pred_off, const int32_t* targ_idx);
 
+/* Same as di_upload_matrix but from RAW counts raw[N][G] (dtype DI_DTYPE_F32 or DI_DTYPE_F64): the device computes
+ * norm = (float)log1p((double)raw) -- np.log1p(raw).astype(np.float32), multinet.py:217 -- in one pass and keeps the
+ * counts resident for di_impute.  Replaces the host-side float64 log1p of fit (:217) and predict (:271). */
+int di_upload_counts(di_handle* h, const void* raw, int32_t dtype, int64_t n_cells, int64_t n_genes);
+
 /* Row numbers (into norm) of training and held-out cells (multinet.py:228-229). */
 int di_set_split(di_handle* h, const int32_t* train_rows, int64_t n_train,
                  const int32_t* test_rows, int64_t n_test);
@@ -106,6 +118,20 @@ int di_validation_loss(di_handle* h, float* val_loss_out);
 int di_predict(di_handle* h, const int32_t* rows, int64_t n, float* out);
 int di_predict_device(di_handle* h, const int32_t* rows, int64_t n, float* d_out, int64_t ld_out);
 
+/* The whole of MultiNet.predict after the gathers (multinet.py:278-303), fused: inference forward of every sub-network,
+ * mean over prediction columns that target the same gene (:284), imputed = log1p(raw) with the target genes replaced
+ * (:286-287), values above 2*max(log1p(raw)) or NaN set to 0 (:291), expm1 (:293), then the policy (:295-302).
+ * out[N][G] (DI_DTYPE_F64 like the reference's DataFrame, or DI_DTYPE_F32) may be pageable or page-locked host memory
+ * (or device memory); chunks of cells are imputed while the previous chunk is copied out.  Needs di_upload_counts.
+ *   slot_gene[n_slots]: gene column predicted by column k of the prediction matrix (negative = ignore the column);
+ *                       NULL = the handle's own targets (targ_idx of di_set_partition, n_slots = S*O).
+ *   d_pred:             NULL = run the forward pass of this handle; otherwise a DEVICE matrix [N][ld_pred] holding
+ *                       n_slots prediction columns (e.g. the all-gathered blocks of a sub-network-sharded model),
+ *                       and slot_gene is required.
+ * Arithmetic is float64 where numpy's is (log1p/expm1 of CUDA's libm: within 2 ulp of glibc's). */
+int di_impute(di_handle* h, int32_t policy, const int32_t* slot_gene, int64_t n_slots, const float* d_pred,
+              int64_t ld_pred, int32_t out_dtype, void* out);
+
 /* Predictor selection (the O(G^2 N) step of fit).  |Pearson r| between genes on RAW
  * counts raw[n_cells][n_genes] -- get_distance_matrix, multinet.py:20-34: abs(np.corrcoef(raw.T)), NaN -> 0 -- and for
  * every target gene targ[s][o] the ntop (<= 8) most correlated candidates that are not targets of sub-network s --
@@ -132,13 +158,14 @@ int64_t di_launch_count(const di_handle* h);
 float di_last_device_ms(const di_handle* h);
 /* Average CUDA-event duration (ms) of the kernel named `which` over the last di_train_epoch, measured on the
  * handle's stream when profiling is enabled with di_set_profiling(h, 1); -1 if unknown.
- * names: "gather", "fwd1", "fwd2", "bwd", "adam" (tensor-core modes; "adam2", "adam1", "bias" in fp32 mode), "infer1", "infer2".
+ * names: "gather", "log1p", "impute", "fwd1", "fwd2", "bwd", "adam" (tensor-core modes; "adam2", "adam1", "bias" in fp32 mode), "infer1", "infer2".
  * di_kernel_launches: how many launches of that kernel the average covers. */
 int di_set_profiling(di_handle* h, int32_t on);
 float di_kernel_ms(const di_handle* h, const char* which);
 int64_t di_kernel_launches(const di_handle* h, const char* which);
 /* Copies an internal activation buffer of the last training step to the host (parity debugging):
- * which = "h" [B][S*Hp], "dz2" [B][S*Op], "dz1" [B][S*Hp]; *ld receives the row pitch in floats. */
+ * which = "h" [B][S*Hp], "dz2" [B][S*Op], "dz1" [B][S*Hp], or "norm" [N][G] (the resident normalised matrix);
+ * *ld receives the row pitch in floats. */
 int di_debug_read(di_handle* h, const char* which, float* out, int64_t capacity_floats, int64_t* ld);
 int di_version(void);
 /* 1 if this build carries kernels for the DI_MATH_* mode, else 0 (di_create then fails with DI_ERR_ARG). */

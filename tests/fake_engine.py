@@ -5,6 +5,7 @@ without a GPU, including world-size-2 gloo runs.  The product never imports this
 import numpy as np
 
 from oracle.multinet_oracle import OracleNet, epoch_permutation, stage
+from oracle.postprocess_oracle import impute_tail, log1p_norm
 
 
 class _History:
@@ -25,6 +26,15 @@ class FakeEngine:
     def set_data(self, norm, pred_idx, targ_idx):
         self.norm, self.pred_idx, self.targ_idx = np.asarray(norm, np.float32), pred_idx, np.asarray(targ_idx)
         self.n_cells = self.norm.shape[0]
+
+    def set_counts(self, raw, pred_idx, targ_idx):
+        self.raw = np.asarray(raw)
+        self.set_data(log1p_norm(self.raw), pred_idx, targ_idx)
+
+    def impute(self, policy="restore", pred=None, slot_gene=None, **_):
+        if pred is None:
+            pred, slot_gene = self.predict(), np.asarray(self.targ_idx).reshape(-1)
+        return impute_tail(self.raw, np.asarray(pred), slot_gene, policy)
 
     def fit(self, train_rows, test_rows, epochs, patience=5, verbose=0, perm_fn=None, on_epoch_end=None):
         Xtr, Ytr = stage(self.norm, self.pred_idx, self.targ_idx, train_rows)
