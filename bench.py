@@ -489,6 +489,32 @@ def main():
                 "TFLOP/s": round(2.0 * G * G * N / (dev_ms * 1e-3) / 1e12, 2),
                 "overlap_with_setup_selection": round(same, 5),
                 "note": "|corrcoef| of raw counts + per-target top-5 (multinet.py:20-34, :344-365); fp32 CUDA-core Gram kernel"}
+        if world == 1 and wl.get("raw") is not None and os.environ.get("DI_BENCH_IMPUTE", "1") != "0":
+            # SURVEY.md 8f rows 2+3, outside every timed region above: raw counts up, log1p on the device, then the fused
+            # tail of MultiNet.predict (forward + duplicate mean + clamp + expm1 + restore) into a float64 [N, G] host matrix
+            raw_np = wl["raw"].numpy()
+            imputed = torch.empty((N, G), dtype=torch.float64, pin_memory=True).numpy()
+            eng.set_profiling(True)
+            t0 = time.perf_counter()
+            eng.set_counts(raw_np, pred_idx, targ_idx)
+            t1 = time.perf_counter()
+            eng.impute(policy="restore", out=imputed)
+            t2 = time.perf_counter()
+            log1p_ms, impute_ms, n_imp = eng.kernel_ms("log1p"), eng.kernel_ms("impute"), eng.kernel_launches("impute")
+            eng.set_profiling(False)
+            kept = bool(np.array_equal(imputed[:64][raw_np[:64] > 0], raw_np[:64][raw_np[:64] > 0].astype(np.float64)))
+            line["postprocess"] = {
+                "upload_counts_s": round(t1 - t0, 4), "impute_s": round(t2 - t1, 4),
+                "log1p_kernel": {"ms": round(log1p_ms, 4), "GB/s": round(8.0 * N * G / (log1p_ms * 1e-3) / 1e9, 1),
+                                 "algorithmic_bytes": 8 * N * G},
+                "impute_kernel": {"ms_per_chunk": round(impute_ms, 4), "chunks": n_imp,
+                                  "GB/s": round((12.0 * N * G + 4.0 * N * S_all * OUT) / (impute_ms * n_imp * 1e-3) / 1e9, 1),
+                                  "algorithmic_bytes": int(12 * N * G + 4 * N * S_all * OUT)},
+                "d2h_bytes": int(8 * N * G), "d2h_GB/s_incl_forward": round(8.0 * N * G / (t2 - t1) / 1e9, 1),
+                "restore_keeps_observed_counts": kept,
+                "note": "di_upload_counts + di_impute (multinet.py:217/:271 and :278-303); float64 [N, G] out like the "
+                        "reference's DataFrame; the host-side pandas route needs several N x G float64 temporaries"}
+            del imputed
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference(wl, args.epochs).items()
                                     if k not in ("t_fit_s", "t_predict_s", "sampled_s")}

@@ -26,13 +26,24 @@ template <typename T> struct Vec;
 template <> struct Vec<float>  { using type = float4;  static constexpr int n = 4; };
 template <> struct Vec<double> { using type = double2; static constexpr int n = 2; };
 
-__device__ __forceinline__ float norm_of(double c) { return (float)log1p(c); }
+// float64 log1p costs ~100 fp64 instructions; counts are overwhelmingly small integers, so each block first tabulates
+// (float)log1p((double)k) for k < kTab with the very same expression and looks those values up (bit-identical
+// results, the kernel becomes bandwidth-bound); anything else -- large, fractional, negative, NaN -- is computed.
+constexpr int kTab = 1024;
+__device__ __forceinline__ float norm_direct(double c) { return (float)log1p(c); }
+__device__ __forceinline__ float norm_of(double c, const float* tab) {
+    const int k = (int)c;                                  // saturating / NaN -> 0 conversion, checked below
+    return ((unsigned)k < (unsigned)kTab && (double)k == c) ? tab[k] : norm_direct(c);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) counts_to_norm_kernel(const T* __restrict__ raw, float* __restrict__ norm,
                                                                   int64_t n, unsigned long long* max_bits) {
     using V = typename Vec<T>::type;
     constexpr int VN = Vec<T>::n;
+    __shared__ float tab[kTab];
+    for (int k = threadIdx.x; k < kTab; k += kThreads) tab[k] = norm_direct((double)k);
+    __syncthreads();
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t nvec = n / VN;
@@ -43,16 +54,17 @@ __global__ void __launch_bounds__(kThreads) counts_to_norm_kernel(const T* __res
         if constexpr (VN == 4) {
             const double a = v.x, b = v.y, c = v.z, d = v.w;
             best = fmax(best, fmax(fmax(a, b), fmax(c, d)));
-            __stcs(reinterpret_cast<float4*>(norm) + i, make_float4(norm_of(a), norm_of(b), norm_of(c), norm_of(d)));
+            __stcs(reinterpret_cast<float4*>(norm) + i,
+                   make_float4(norm_of(a, tab), norm_of(b, tab), norm_of(c, tab), norm_of(d, tab)));
         } else {
             best = fmax(best, fmax((double)v.x, (double)v.y));
-            __stcs(reinterpret_cast<float2*>(norm) + i, make_float2(norm_of(v.x), norm_of(v.y)));
+            __stcs(reinterpret_cast<float2*>(norm) + i, make_float2(norm_of(v.x, tab), norm_of(v.y, tab)));
         }
     }
     for (int64_t i = nvec * VN + tid; i < n; i += nthreads) {
         const double c = (double)raw[i];
         best = fmax(best, c);
-        norm[i] = norm_of(c);
+        norm[i] = norm_of(c, tab);
     }
     // non-negative doubles order like their bit patterns; fmax drops NaN and best starts at 0
     unsigned long long bits = (unsigned long long)__double_as_longlong(best);
@@ -77,10 +89,15 @@ __global__ void __launch_bounds__(kThreads) impute_kernel(const float* __restric
     const int2 ent = gene_ent[g];
     for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
         const TRaw c = __ldcs(raw + r * G + g);
+        if (policy == DI_POLICY_RESTORE && c > (TRaw)0) {      // observed counts are kept whatever was predicted (:295-298)
+            __stcs(out + r * G + g, (TOut)c);
+            continue;
+        }
         double v;
         if (ent.y == 0) {
-            // not a target: the reference carries float64 log1p(raw) through expm1 (multinet.py:286-287, :293)
-            v = log1p((double)c);
+            // not a target: the reference carries float64 log1p(raw) through expm1 (multinet.py:286-287, :293);
+            // a zero count stays exactly zero through log1p, the clamp test and expm1
+            v = (c == (TRaw)0) ? 0.0 : log1p((double)c);
         } else {
             // groupby-mean of float32 columns (:284) as pandas computes it: NaN entries are skipped, the sum is a
             // Kahan sum in float32 over the columns in ascending order, divided by the count in float32
@@ -101,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) impute_kernel(const float* __restric
             v = n ? (double)(sum / (float)n) : (double)NAN;
         }
         if (v > clamp || isnan(v)) v = 0.0;              // "to prevent overflow" (:291)
-        v = expm1(v);                                    // back to counts (:293)
+        if (v != 0.0) v = expm1(v);                      // back to counts (:293); expm1(0) = 0
         if (policy == DI_POLICY_RESTORE) { if (c > (TRaw)0) v = (double)c; }            // :295-298
         else if (policy == DI_POLICY_MAX) { if ((double)c > v) v = (double)c; }         // :299-302
         __stcs(out + r * G + g, (TOut)v);

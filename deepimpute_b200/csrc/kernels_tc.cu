@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "engine.h"
 #include "tc_common.cuh"
@@ -73,6 +74,8 @@ struct TcParams {
     float* DZ2; float* DZ1;                      // [Bp][S*Op], [Bp][S*Hp]
     float *Hlo, *DZ2lo, *DZ1lo;                  // TF32 residual twins of h / dz2 / dz1 (nullptr: not wanted)
     float *b1, *mb1, *vb1, *b2, *mb2, *vb2;
+    float *W1, *mW1, *vW1, *W2, *mW2, *vW2;      // ADAM, direct mode: updated values go to global memory from registers
+    int adam_direct;                             // 1: registers -> st.global; 0: in place in the ring + TMA stores
     float* out; int64_t ld_out;                  // inference output
     double* loss;
     int n_valid;                                 // real rows of the batch / chunk
@@ -501,21 +504,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
                 for (int kb = 0; kb < nkb; ++kb)
                     load_stage<true>(sB + (size_t)kb * b_block_bytes, m, &ops_bar, b_c0, b_c1 + kb * BLOCK_K, p.n_cols);
             };
+            // X3 rounds: dout_hi in_lo, dout_hi in_hi, dout_lo in_hi -- every operand is fetched exactly once and a
+            // round reloads only the buffer whose contents change (non-X3: Blo aliases B, one round)
             mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * (A_STAGE_BYTES + b_block_bytes));
-            load_a(&mapA); load_b(&mapB);                          // round 0: dout_hi, in_hi
+            load_a(&mapA); load_b(&mapBlo);                        // round 0: dout_hi, in_lo
             for (int c = 0; c < min(AD_STAGES, nchunks); ++c) load_chunk(c);
             if constexpr (X3) {
                 mbar_wait(&mma_bar, 0, 9);                         // round 0 MMAs have read the buffers
                 mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * b_block_bytes);
-                load_b(&mapBlo);                                   // round 1: dout_hi (kept), in_lo
+                load_b(&mapB);                                     // round 1: dout_hi (kept), in_hi
                 mbar_wait(&mma_bar, 1, 9);
-                mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * (A_STAGE_BYTES + b_block_bytes));
-                load_a(&mapAlo); load_b(&mapB);                    // round 2: dout_lo, in_hi
+                mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * A_STAGE_BYTES);
+                load_a(&mapAlo);                                   // round 2: dout_lo, in_hi (kept)
             }
             if (ring > AD_STAGES) {                                // the operand buffers join the ring
                 mbar_wait(&tmem_full_bar, 0, 4);
                 for (int c = AD_STAGES; c < min(ring, nchunks); ++c) load_chunk(c);
             }
+            if (p.adam_direct) {
+                // the epilogue threads store their results to global memory themselves: a stage is free again as soon
+                // as all 128 of them hold its chunk in registers
+                for (int c = 0; c + ring < nchunks; ++c) {
+                    mbar_wait(&wdone[c % ring], (c / ring) & 1, 8);
+                    load_chunk(c + ring);
+                }
+            } else {
             for (int c = 0; c < nchunks; ++c) {
                 const int st = c % ring;
                 float* ws = stage_ptr(st);
@@ -532,6 +545,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
                     bulk_wait_read<1>();
                     load_chunk(c - 1 + ring);
                 }
+            }
             }
             bulk_wait<0>();
         }
@@ -584,12 +598,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
                 }
 #pragma unroll
                 for (int r = 0; r < AD_R; ++r) adam_update_fast(g[r], w[r], m[r], v[r], adam);
+                if (p.adam_direct) {
+                    // the updates consumed every loaded value, so the stage can be refilled; results leave from
+                    // registers: a warp writes 128 contiguous bytes per instruction, 24 independent stores in flight
+                    mbar_arrive(&wdone[st]);
+                    const int64_t off = (row_base + n0 + (int64_t)c * AD_R) * out_dim + m0 + fl;
+                    float* gw = (second ? p.W2 : p.W1) + off;
+                    float* gm = (second ? p.mW2 : p.mW1) + off;
+                    float* gv = (second ? p.vW2 : p.vW1) + off;
+#pragma unroll
+                    for (int r = 0; r < AD_R; ++r) {
+                        gw[(int64_t)r * out_dim] = w[r];
+                        gm[(int64_t)r * out_dim] = m[r];
+                        gv[(int64_t)r * out_dim] = v[r];
+                    }
+                    if (c < 40 && threadIdx.x == 0) DI_TRACE(48 + c);
+                    continue;
+                }
 #pragma unroll
                 for (int r = 0; r < AD_R; ++r) {
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + r * row_b), "f"(w[r]) : "memory");
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + tile_b + r * row_b), "f"(m[r]) : "memory");
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 2 * tile_b + r * row_b), "f"(v[r]) : "memory");
                 }
+            } else if (p.adam_direct) {
+                mbar_arrive(&wdone[st]);                  // padding feature: nothing to update, the stage still needs 128 arrivals
+                continue;
             }
             fence_proxy_async();                          // generic-proxy writes -> visible to the TMA store
             mbar_arrive(&wdone[st]);
@@ -636,6 +670,7 @@ struct TcState {
     bool x3 = false;                                       // forward GEMMs error-compensated (DI_MATH_TF32X3)
     bool x3_bwd = false, simt_adam = false;                // experiments (DEEPIMPUTE_B200_EXPERIMENT bit 0 / bit 1)
     int aux_h = 0, aux_y = 0, wbox1 = 0, wbox2 = 0;
+    bool adam_direct = true;                               // DEEPIMPUTE_B200_ADAM_STORE=tma selects the in-place ring + TMA stores
 };
 
 void drop_epoch_graph(TcState* st) {
@@ -743,6 +778,7 @@ bool tc_init(Engine& e) {
     const int aux_floats = e.Bp * TILE_M;
     st->x3_bwd = st->x3;
     if (const char* v = getenv("DEEPIMPUTE_B200_EXPERIMENT")) st->simt_adam = atoi(v) & 2;
+    if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_STORE")) st->adam_direct = strcmp(v, "tma") != 0;
     for (int deep = 0; deep < 2; ++deep) {
         st->fwd1_train[deep] = pick_cfg(e.Bp, 0, st->x3, deep);
         st->fwd2_train[deep] = pick_cfg(e.Bp, (st->x3 && !deep) ? 0 : aux_floats, st->x3, deep);
@@ -898,6 +934,8 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     TcParams q = p;
     q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;
     q.row0 = a.row0; q.wbox = st->wbox1; q.wbox2 = st->wbox2;
+    q.W1 = e.W1; q.mW1 = e.mW1; q.vW1 = e.vW1; q.W2 = e.W2; q.mW2 = e.mW2; q.vW2 = e.vW2;
+    q.adam_direct = st->adam_direct ? 1 : 0;
     if (!pl.graph && st->d_trace) q.trace = st->d_trace + 768;
     int maxPp = 0;
     for (int s = pl.s0; s < pl.s0 + pl.ns; ++s) maxPp = std::max(maxPp, e.Pp[s]);

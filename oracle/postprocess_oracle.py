@@ -17,7 +17,11 @@ import pandas as pd
 
 
 def log1p_norm(raw):
-    return np.log1p(np.asarray(raw)).astype(np.float32)
+    """``np.log1p(raw).astype(np.float32)`` as the reference evaluates it on its float64 frames (``pd.read_csv`` gives
+    float64 / int64 columns, so numpy's float64 ``log1p`` runs and the result is rounded once).  A float32 frame would
+    send numpy down ``log1pf`` (not correctly rounded, up to 1 float32 ulp away); the device always computes the
+    float64 form, so that is what the oracle states for every input dtype."""
+    return np.log1p(np.asarray(raw, dtype=np.float64)).astype(np.float32)
 
 
 def impute_tail(raw, predicted, slot_gene, policy="restore"):
