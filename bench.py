@@ -205,8 +205,8 @@ def load_traffic(workload, kernel, n_pred):
     grids = {"adam": (cd(max_pp, 128) + cd(HIDDEN, 128), max(cd(OUT, 128), cd(HIDDEN, 128)), S),
              "adam2": (cd(HIDDEN, 128), cd(OUT, 128), S), "adam1": (cd(max_pp, 128), cd(HIDDEN, 128), S),
              "fwd1": (1, cd(HIDDEN, 128), S), "fwd2": (1, cd(OUT, 128), S), "bwd": (1, cd(HIDDEN, 128), S)}
-    names = {"adam": "tc_adam_kernel", "adam2": "tc_adam_kernel", "adam1": "tc_adam_kernel", "fwd1": "tc_kernel<0", "fwd2": "tc_kernel<1",
-             "bwd": "tc_kernel<2"}
+    names = {"adam": ("tc_adam_big_kernel", "tc_adam_kernel"), "adam2": "tc_adam_kernel", "adam1": "tc_adam_kernel",
+             "fwd1": "tc_kernel<0", "fwd2": "tc_kernel<1", "bwd": "tc_kernel<2"}
     if kernel not in grids:
         return None
     want = "grid ({}, {}, {})".format(*grids[kernel])

@@ -76,6 +76,7 @@ struct TcParams {
     float *b1, *mb1, *vb1, *b2, *mb2, *vb2;
     float *W1, *mW1, *vW1, *W2, *mW2, *vW2;      // ADAM, direct mode: updated values go to global memory from registers
     int adam_direct;                             // 1: registers -> st.global; 0: in place in the ring + TMA stores
+    int ad_nded, ad_stride;                      // one-CTA-per-SM ADAM kernel: dedicated chunk stages, bytes per stage
     float* out; int64_t ld_out;                  // inference output
     double* loss;
     int n_valid;                                 // real rows of the batch / chunk
@@ -637,6 +638,179 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     DI_TRACE_T0(5);
 }
 
+// ------------------------------------------------------------------------------------------ ADAM, one CTA per SM
+// Same tile and arithmetic as tc_adam_kernel, laid out for ONE resident CTA per SM that never waits on a buffer:
+//   * every operand set is resident at once (X3: dout_hi, in_lo, in_hi, dout_lo), so the three compensation rounds
+//     are issued back to back -- the ring kernel reloads two of its buffers between rounds and spends a third of its
+//     life (about 10k of 31k cycles, in-kernel trace) waiting for TMA before the accumulator is complete;
+//   * every [8 rows x 128 features] x {w, m, v} chunk of the tile owns a shared-memory stage (n_ded dedicated ones
+//     are filled while the MMAs run, the rest reuse the operand area once the accumulator is complete), so there is no
+//     refill protocol at all;
+//   * eight epilogue warps (two per TMEM lane quadrant) take alternate chunks and write w, m, v to global memory
+//     straight from registers.
+// 320 threads: warps 0-7 epilogue, warp 8 TMA, warp 9 MMA.  Needs 4 (X3) or 2 operand sets of nkb x 16 KB each:
+// used when that fits (batch <= 64 in X3 mode), otherwise the ring kernel above runs.
+constexpr int NTHREADS_BIG = 320;
+constexpr int AD_MAX_CHUNKS = ADAM_TILE / AD_R;
+
+template <bool X3>
+__global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __grid_constant__ AdamMaps maps1,
+                                                                       const __grid_constant__ AdamMaps maps2, const TcParams p) {
+    const int s = blockIdx.z + p.s_base;
+    const SubnetDesc d = p.desc[s];
+    const bool second = (int)blockIdx.x >= p.nx1;
+    const AdamMaps* mp = second ? &maps2 : &maps1;
+    const CUtensorMap &mapA = mp->A, &mapB = mp->B, &mapAlo = mp->Alo, &mapBlo = mp->Blo, &mapW = mp->W, &mapM = mp->M, &mapV = mp->V;
+    const int m0 = blockIdx.y * TILE_M;
+    const int n0 = ((int)blockIdx.x - (second ? p.nx1 : 0)) * p.n_cols;
+    int out_dim, in_dim, a_c0, b_c0, b_c1;
+    int64_t row_base;
+    if (!second) { out_dim = p.Hp; in_dim = d.Pp; a_c0 = s * p.Hp + m0; b_c0 = (int)d.coff + n0; b_c1 = (int)p.row0; row_base = d.coff; }
+    else { out_dim = p.Op; in_dim = p.Hp; a_c0 = s * p.Op + m0; b_c0 = s * p.Hp + n0; b_c1 = 0; row_base = (int64_t)s * p.Hp; }
+    if (m0 >= out_dim || n0 >= in_dim) return;
+    const int nkb = p.nkb_adam;
+    const int nchunks = min(p.n_cols, in_dim - n0) / AD_R;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int NSETS = X3 ? 4 : 2;
+    const uint32_t set_bytes = (uint32_t)nkb * A_STAGE_BYTES;       // n_cols == TILE_M: A and B sets have one size
+    uint8_t* set0 = smem;                                           // dout_hi
+    uint8_t* set1 = smem + set_bytes;                               // in_lo   (plain TF32: in)
+    uint8_t* set2 = smem + 2 * (size_t)set_bytes;                   // in_hi
+    uint8_t* set3 = smem + 3 * (size_t)set_bytes;                   // dout_lo
+    uint8_t* ded = smem + (size_t)NSETS * set_bytes;                // dedicated chunk stages
+    const int wbox = second ? p.wbox2 : p.wbox;
+    const int tile_floats = AD_R * wbox;
+    const uint32_t chunk_bytes = 3u * tile_floats * 4u;
+    auto stage_ptr = [&](int c) -> float* {
+        return reinterpret_cast<float*>(c < p.ad_nded ? ded + (size_t)c * p.ad_stride : smem + (size_t)(c - p.ad_nded) * p.ad_stride);
+    };
+    __shared__ uint64_t ops_bar[2], tmem_full_bar, wfull[AD_MAX_CHUNKS];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DI_TRACE_T0(0);
+    if (threadIdx.x == 0) {
+        mbar_init(&ops_bar[0], 1); mbar_init(&ops_bar[1], 1); mbar_init(&tmem_full_bar, 1);
+        for (int i = 0; i < AD_MAX_CHUNKS; ++i) mbar_init(&wfull[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    if (warp == 8) {
+        if (elect_one()) {
+            auto load_a = [&](const CUtensorMap* m, uint8_t* dst, uint64_t* bar) {
+                for (int kb = 0; kb < nkb; ++kb)
+                    load_stage<true>(dst + (size_t)kb * A_STAGE_BYTES, m, bar, a_c0, kb * BLOCK_K, TILE_M);
+            };
+            auto load_b = [&](const CUtensorMap* m, uint8_t* dst, uint64_t* bar) {
+                for (int kb = 0; kb < nkb; ++kb)
+                    load_stage<true>(dst + (size_t)kb * A_STAGE_BYTES, m, bar, b_c0, b_c1 + kb * BLOCK_K, p.n_cols);
+            };
+            auto load_chunk = [&](int c) {
+                float* ws = stage_ptr(c);
+                const int32_t r = (int32_t)(row_base + n0 + c * AD_R);
+                mbar_arrive_expect_tx(&wfull[c], chunk_bytes);
+                tma_load_2d(ws, &mapW, &wfull[c], m0, r);
+                tma_load_2d(ws + tile_floats, &mapM, &wfull[c], m0, r);
+                tma_load_2d(ws + 2 * tile_floats, &mapV, &wfull[c], m0, r);
+            };
+            if constexpr (X3) {
+                mbar_arrive_expect_tx(&ops_bar[0], 3u * set_bytes);
+                load_a(&mapA, set0, &ops_bar[0]); load_b(&mapBlo, set1, &ops_bar[0]); load_b(&mapB, set2, &ops_bar[0]);
+                mbar_arrive_expect_tx(&ops_bar[1], set_bytes);
+                load_a(&mapAlo, set3, &ops_bar[1]);
+            } else {
+                mbar_arrive_expect_tx(&ops_bar[0], 2u * set_bytes);
+                load_a(&mapA, set0, &ops_bar[0]); load_b(&mapB, set1, &ops_bar[0]);
+            }
+            for (int c = 0; c < min(p.ad_nded, nchunks); ++c) load_chunk(c);
+            if (nchunks > p.ad_nded) {                             // the operand area becomes chunk stages
+                mbar_wait(&tmem_full_bar, 0, 4);
+                for (int c = p.ad_nded; c < nchunks; ++c) load_chunk(c);
+            }
+        }
+    } else if (warp == 9) {
+        if (elect_one()) {
+            const uint32_t idesc = idesc_for(p.n_cols, true, true);
+            auto mma_round = [&](const uint8_t* a, const uint8_t* b, bool first) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint32_t sa = smem_u32(a + (size_t)kb * A_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(b + (size_t)kb * A_STAGE_BYTES);
+#pragma unroll
+                    for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
+                        umma_tf32(tmem, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (!first || kb || j) ? 1u : 0u);
+                }
+            };
+            mbar_wait(&ops_bar[0], 0, 6);
+            tc_fence_after();
+            mma_round(set0, set1, true);                               // dout_hi in_lo   (plain TF32: dout in)
+            if constexpr (X3) {
+                mma_round(set0, set2, false);                          // dout_hi in_hi
+                mbar_wait(&ops_bar[1], 0, 6);
+                tc_fence_after();
+                mma_round(set3, set2, false);                          // dout_lo in_hi
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        const int quad = warp & 3, grp = warp >> 2;       // TMEM lane quadrant of this warp; chunks c = grp, grp + 2, ...
+        const int fl = quad * 32 + lane;
+        const bool f_ok = (m0 + fl) < out_dim;
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16);
+        const AdamParams adam = adam_of(p);
+        const bool tracer = p.trace && quad == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+        DI_TRACE_T0(2);
+        mbar_wait(&tmem_full_bar, 0, 4);
+        tc_fence_after();
+        DI_TRACE_T0(3);
+        float* gw0 = second ? p.W2 : p.W1;
+        float* gm0 = second ? p.mW2 : p.mW1;
+        float* gv0 = second ? p.vW2 : p.vW1;
+        for (int c = grp; c < nchunks; c += 2) {
+            float g[AD_R];
+            __syncwarp();
+            tmem_ld8(taddr + c * AD_R, g);
+            mbar_wait(&wfull[c], 0, 7);
+            if (tracer && c < 40) p.trace[8 + c] = clock64();
+            __syncwarp();
+            if (f_ok) {
+                const uint32_t base = smem_u32(stage_ptr(c)) + (uint32_t)fl * 4u;
+                const uint32_t row_b = (uint32_t)wbox * 4u, tile_b = (uint32_t)tile_floats * 4u;
+                float w[AD_R], m[AD_R], v[AD_R];
+#pragma unroll
+                for (int r = 0; r < AD_R; ++r) {
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[r]) : "r"(base + r * row_b));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m[r]) : "r"(base + tile_b + r * row_b));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[r]) : "r"(base + 2 * tile_b + r * row_b));
+                }
+#pragma unroll
+                for (int r = 0; r < AD_R; ++r) adam_update_fast(g[r], w[r], m[r], v[r], adam);
+                const int64_t off = (row_base + n0 + (int64_t)c * AD_R) * out_dim + m0 + fl;
+#pragma unroll
+                for (int r = 0; r < AD_R; ++r) {
+                    gw0[off + (int64_t)r * out_dim] = w[r];
+                    gm0[off + (int64_t)r * out_dim] = m[r];
+                    gv0[off + (int64_t)r * out_dim] = v[r];
+                }
+            }
+            if (tracer && c < 40) p.trace[48 + c] = clock64();
+        }
+        __syncwarp();
+        DI_TRACE_T0(4);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+    DI_TRACE_T0(5);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct TcState {
     // weights / step buffers (fixed for the life of the engine)
@@ -671,6 +845,8 @@ struct TcState {
     bool x3_bwd = false, simt_adam = false;                // experiments (DEEPIMPUTE_B200_EXPERIMENT bit 0 / bit 1)
     int aux_h = 0, aux_y = 0, wbox1 = 0, wbox2 = 0;
     bool adam_direct = true;                               // DEEPIMPUTE_B200_ADAM_STORE=tma selects the in-place ring + TMA stores
+    bool adam_big = false;                                 // one-CTA-per-SM ADAM kernel (DEEPIMPUTE_B200_ADAM=ring disables it)
+    int smem_adam_big = 0, ad_nded = 0, ad_stride = 0;
 };
 
 void drop_epoch_graph(TcState* st) {
@@ -819,6 +995,16 @@ bool tc_init(Engine& e) {
         cudaMalloc((void**)&st->d_step_base, sizeof(uint32_t)) != cudaSuccess) { e.err = "epoch-graph set-up failed"; return false; }
     const int nkb = e.Bp / BLOCK_K;
     st->smem_adam = nkb * (int)(A_STAGE_BYTES + ADAM_TILE * BLOCK_K * 4) + AD_STAGES * 3 * AD_R * TILE_M * 4 + 1024;
+    {   // one-CTA-per-SM variant: all operand sets resident + a stage per chunk
+        const int nsets = st->x3 ? 4 : 2;
+        const int ops = nsets * nkb * (int)A_STAGE_BYTES;
+        st->ad_stride = 3 * AD_R * std::max(st->wbox1, st->wbox2) * 4;
+        const int room = 227 * 1024 - 1024 - ops;
+        st->ad_nded = room > 0 ? std::min(AD_MAX_CHUNKS, room / st->ad_stride) : 0;
+        st->adam_big = st->ad_nded >= 1 && (AD_MAX_CHUNKS - st->ad_nded) * st->ad_stride <= ops;
+        st->smem_adam_big = ops + st->ad_nded * st->ad_stride + 1024;
+        if (const char* v = getenv("DEEPIMPUTE_B200_ADAM")) if (!strcmp(v, "ring")) st->adam_big = false;
+    }
     if (st->smem_adam > 227 * 1024 || !st->fwd1_train[0].stages || !st->fwd2_train[0].stages || !st->bwd_train[0].stages ||
         !st->fwd1_train[1].stages || !st->fwd2_train[1].stages || !st->bwd_train[1].stages || !st->infer.stages) {
         e.err = "tensor-core math modes: this batch size needs more shared memory than one SM has (use math mode fp32)";
@@ -837,6 +1023,10 @@ bool tc_init(Engine& e) {
     set((const void*)tc_kernel<TC_BWD, true>, m3);
     set((const void*)tc_adam_kernel<false>, st->smem_adam);
     set((const void*)tc_adam_kernel<true>, st->smem_adam);
+    if (st->adam_big) {
+        set((const void*)tc_adam_big_kernel<false>, st->smem_adam_big);
+        set((const void*)tc_adam_big_kernel<true>, st->smem_adam_big);
+    }
     if (ce != cudaSuccess) { e.err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return false; }
     return true;
 }
@@ -949,7 +1139,11 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
         m2.Alo = st->DZ2lo_mn; m2.Blo = st->Hlo_mn;
     } else { m1.Alo = m1.A; m1.Blo = m1.B; m2.Alo = m2.A; m2.Blo = m2.B; }
     KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam");
-    if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, pl.main>>>(m1, m2, q);
+    q.ad_nded = st->ad_nded; q.ad_stride = st->ad_stride;
+    if (st->adam_big) {
+        if (st->x3) tc_adam_big_kernel<true><<<grid, NTHREADS_BIG, st->smem_adam_big, pl.main>>>(m1, m2, q);
+        else tc_adam_big_kernel<false><<<grid, NTHREADS_BIG, st->smem_adam_big, pl.main>>>(m1, m2, q);
+    } else if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, pl.main>>>(m1, m2, q);
     else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, pl.main>>>(m1, m2, q);
     if (t) { delete t; count_launch(e, "adam"); }
 }

@@ -26,7 +26,9 @@ def log1p_norm(raw):
 
 def impute_tail(raw, predicted, slot_gene, policy="restore"):
     """raw [N, G] counts; predicted [N, n_slots] float32, column k predicts gene ``slot_gene[k]``.  Returns float64 [N, G]."""
-    raw = pd.DataFrame(np.asarray(raw))
+    # float64 frame, as pd.read_csv delivers it (a float32 frame would make numpy carry log1pf results in float32 through
+    # :271-:293; the device states the float64 form for every input dtype, see log1p_norm)
+    raw = pd.DataFrame(np.asarray(raw, dtype=np.float64))
     norm_raw = np.log1p(raw)                                                    # :271
     predicted = pd.DataFrame(np.asarray(predicted, dtype=np.float32), columns=np.asarray(slot_gene))
     predicted = predicted.T.groupby(level=0).mean().T                           # :284 (axis=1 groupby, pandas-3 spelling)
