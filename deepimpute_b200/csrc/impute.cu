@@ -130,7 +130,9 @@ void impute_dispatch(Engine& e, const float* pred, int64_t ld_pred, int64_t row0
                      int policy, int out_dtype, void* out) {
     const int2* ent = reinterpret_cast<const int2*>(e.d_gene_off);
     const TRaw* raw = static_cast<const TRaw*>(e.d_raw) + row0 * e.G;
-    dim3 grid((unsigned)((e.G + kThreads - 1) / kThreads), (unsigned)std::min<int64_t>(rows, 32768));
+    // gene tiles x row lanes: about 16 resident blocks per SM in total, every thread walks rows with stride grid.y
+    const int64_t gx = (e.G + kThreads - 1) / kThreads;
+    dim3 grid((unsigned)gx, (unsigned)std::max<int64_t>(1, std::min<int64_t>(rows, (148 * 16 + gx - 1) / gx)));
     if (out_dtype == DI_DTYPE_F64)
         impute_kernel<TRaw, double><<<grid, kThreads, 0, e.stream>>>(pred, ld_pred, ent, e.d_gene_slots, raw, e.G, rows,
                                                                      clamp, policy, static_cast<double*>(out));

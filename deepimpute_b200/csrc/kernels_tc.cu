@@ -21,7 +21,9 @@
 // TMEM, and TMA bulk stores drain them -- enough bytes in flight per SM to cover HBM latency without registers.
 //
 // Warp roles (192 threads): warps 0-3 epilogue (warp w reads TMEM lanes 32w..32w+31), warp 4 TMA producer,
-// warp 5 MMA issuer.  smem ring of 32-wide K slabs, full/empty mbarriers, one tmem_full barrier.
+// warp 5 MMA issuer.  smem ring of 32-wide K slabs, full/empty mbarriers, one tmem_full barrier.  X3 kernels have
+// four more warps (6-9): all eight non-producer warps compute the residual slabs during the main loop and then split
+// the epilogue (two warps per TMEM lane quadrant, half of the batch columns each).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -177,7 +179,8 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
     const float* aux = reinterpret_cast<const float*>(lo_base + (size_t)lo_stages * stage_bytes);
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], lo_ready[MAX_STAGES], lo_free[MAX_STAGES], tmem_full_bar, aux_bar;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ double red[4];
+    __shared__ double red[8];
+    __shared__ float gpart[TILE_M];      // X3: per-feature partial sums of the upper epilogue warps (bias gradients)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     DI_TRACE_T0(0);
@@ -278,16 +281,20 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
             }
             umma_commit(&tmem_full_bar);
         }
-    } else if (warp >= 6) {
-        if constexpr (X3) convert((warp - 2) * 32 + lane);     // converter-only warps
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = output features m0+32w.. =====
-        const int fl = warp * 32 + lane;                  // feature inside the tile
+        // ===== epilogue: a warp reads the TMEM lanes of its quadrant (warp % 4) = output features m0 + 32 quad .. =====
+        // X3: the four converter-only warps (6-9) share the epilogue with warps 0-3: each quadrant has two warps, the
+        // lower one takes the first half of the batch columns, the upper one the second half
+        const int quad = warp & 3;
+        const bool upper = warp >= 6;
+        const int fl = quad * 32 + lane;                  // feature inside the tile
         const int f = m0 + fl;                            // output feature of this thread
         const bool f_ok = f < out_dim;
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16);
         const int ncol = p.n_cols;
-        if constexpr (X3) convert(warp * 32 + lane);
+        const int c_lo = (X3 && upper) ? ncol / 2 : 0;
+        const int c_hi = (X3 && !upper) ? ncol / 2 : ncol;
+        if constexpr (X3) convert(upper ? (warp - 2) * 32 + lane : warp * 32 + lane);
         if (p.aux_cols > 0) mbar_wait(&aux_bar, 0, 5);
         DI_TRACE_T0(2);
         mbar_wait(&tmem_full_bar, 0, 4);
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
             const uint32_t dstep = dropout_step(p);
             float* hrow = p.Hact + row0 * p.ldh + (int64_t)s * p.Hp + f;
             float* hlo = (p.training && p.Hlo) ? p.Hlo + (int64_t)s * p.Hp + f : nullptr;   // training h starts at row 0
-            for (int c = 0; c < ncol; c += 16) {
+            for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16];
                 __syncwarp();
                 tmem_ld16(taddr + c, v);
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
             const float bias = f_ok ? p.b2[bi] : 0.f;
             float part = 0.f, gsum = 0.f;
             const int rows_left = p.n_valid - row_tile * ncol;
-            for (int c = 0; c < ncol; c += 16) {
+            for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16], y[16];
                 __syncwarp();
                 tmem_ld16(taddr + c, v);
@@ -374,19 +381,27 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                     }
                 }
             }
-            if (p.training && f_ok) adam_update_fast(gsum, p.b2[bi], p.mb2[bi], p.vb2[bi], adam_of(p));
-            if (p.loss) {
+            if (p.training || p.loss) {
                 double dpart = (double)part;
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) dpart += __shfl_xor_sync(0xffffffffu, dpart, off);
-                if (lane == 0) red[warp] = dpart;
-                named_bar_sync(1, 128);
-                if (threadIdx.x == 0) atomicAdd(p.loss, red[0] + red[1] + red[2] + red[3]);
+                if (lane == 0) red[upper ? 4 + quad : quad] = dpart;
+                if (X3 && upper) gpart[fl] = gsum;
+                named_bar_sync(1, X3 ? 256 : 128);
+                if (!upper) {
+                    if constexpr (X3) gsum += gpart[fl];
+                    if (p.training && f_ok) adam_update_fast(gsum, p.b2[bi], p.mb2[bi], p.vb2[bi], adam_of(p));
+                    if (p.loss && threadIdx.x == 0) {
+                        double tot = red[0] + red[1] + red[2] + red[3];
+                        if constexpr (X3) tot += red[4] + red[5] + red[6] + red[7];
+                        atomicAdd(p.loss, tot);
+                    }
+                }
             }
         } else {
             const int64_t bi = (int64_t)s * p.Hp + f;
             float gsum = 0.f;
-            for (int c = 0; c < ncol; c += 16) {
+            for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16], h[16];
                 __syncwarp();
                 tmem_ld16(taddr + c, v);
@@ -411,7 +426,12 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                     for (int i = 0; i < 16; ++i) dlo[(int64_t)i * ld1] = tf32_residual(g[i]);
                 }
             }
-            if (f_ok) adam_update_fast(gsum, p.b1[bi], p.mb1[bi], p.vb1[bi], adam_of(p));
+            if constexpr (X3) {
+                if (upper) gpart[fl] = gsum;
+                named_bar_sync(1, 256);
+                if (!upper) gsum += gpart[fl];
+            }
+            if (!upper && f_ok) adam_update_fast(gsum, p.b1[bi], p.mb1[bi], p.vb1[bi], adam_of(p));
         }
     }
 
@@ -646,11 +666,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
 //   * every [8 rows x 128 features] x {w, m, v} chunk of the tile owns a shared-memory stage (n_ded dedicated ones
 //     are filled while the MMAs run, the rest reuse the operand area once the accumulator is complete), so there is no
 //     refill protocol at all;
-//   * eight epilogue warps (two per TMEM lane quadrant) take alternate chunks and write w, m, v to global memory
-//     straight from registers.
-// 320 threads: warps 0-7 epilogue, warp 8 TMA, warp 9 MMA.  Needs 4 (X3) or 2 operand sets of nkb x 16 KB each:
+//   * 4 x G epilogue warps (G per TMEM lane quadrant, G = 2..4 chosen at launch) take chunks round-robin and write w, m, v to global memory
+//     straight from registers: the update of one chunk is a latency chain (TMEM load, 24 shared loads, 16 MUFU ops,
+//     24 stores) of about 900 cycles per warp, so the number of warps sets the pace.
+// (4 G + 2) warps: 0 .. 4G-1 epilogue, then the TMA warp, then the MMA warp.  Needs 4 (X3) or 2 operand sets of nkb x 16 KB each:
 // used when that fits (batch <= 64 in X3 mode), otherwise the ring kernel above runs.
-constexpr int NTHREADS_BIG = 320;
+constexpr int AD_MAX_GROUPS = 4;                          // epilogue warp groups (4 warps each) taking chunks round-robin
+constexpr int NTHREADS_BIG = (4 * AD_MAX_GROUPS + 2) * 32;   // + TMA warp + MMA warp; the launch may use fewer groups
 constexpr int AD_MAX_CHUNKS = ADAM_TILE / AD_R;
 
 template <bool X3>
@@ -690,6 +712,7 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ngroups = (((int)blockDim.x >> 5) - 2) >> 2;
     DI_TRACE_T0(0);
     if (threadIdx.x == 0) {
         mbar_init(&ops_bar[0], 1); mbar_init(&ops_bar[1], 1); mbar_init(&tmem_full_bar, 1);
@@ -702,7 +725,7 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
 
-    if (warp == 8) {
+    if (warp == 4 * ngroups) {
         if (elect_one()) {
             auto load_a = [&](const CUtensorMap* m, uint8_t* dst, uint64_t* bar) {
                 for (int kb = 0; kb < nkb; ++kb)
@@ -735,7 +758,7 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
                 for (int c = p.ad_nded; c < nchunks; ++c) load_chunk(c);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 4 * ngroups + 1) {
         if (elect_one()) {
             const uint32_t idesc = idesc_for(p.n_cols, true, true);
             auto mma_round = [&](const uint8_t* a, const uint8_t* b, bool first) {
@@ -759,7 +782,7 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
             umma_commit(&tmem_full_bar);
         }
     } else {
-        const int quad = warp & 3, grp = warp >> 2;       // TMEM lane quadrant of this warp; chunks c = grp, grp + 2, ...
+        const int quad = warp & 3, grp = warp >> 2;       // TMEM lane quadrant of this warp; chunks c = grp, grp + ngroups, ...
         const int fl = quad * 32 + lane;
         const bool f_ok = (m0 + fl) < out_dim;
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16);
@@ -772,7 +795,7 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
         float* gw0 = second ? p.W2 : p.W1;
         float* gm0 = second ? p.mW2 : p.mW1;
         float* gv0 = second ? p.vW2 : p.vW1;
-        for (int c = grp; c < nchunks; c += 2) {
+        for (int c = grp; c < nchunks; c += ngroups) {
             float g[AD_R];
             __syncwarp();
             tmem_ld8(taddr + c * AD_R, g);
@@ -846,7 +869,7 @@ struct TcState {
     int aux_h = 0, aux_y = 0, wbox1 = 0, wbox2 = 0;
     bool adam_direct = true;                               // DEEPIMPUTE_B200_ADAM_STORE=tma selects the in-place ring + TMA stores
     bool adam_big = false;                                 // one-CTA-per-SM ADAM kernel (DEEPIMPUTE_B200_ADAM=ring disables it)
-    int smem_adam_big = 0, ad_nded = 0, ad_stride = 0;
+    int smem_adam_big = 0, ad_nded = 0, ad_stride = 0, ad_groups = 4;
 };
 
 void drop_epoch_graph(TcState* st) {
@@ -1004,6 +1027,7 @@ bool tc_init(Engine& e) {
         st->adam_big = st->ad_nded >= 1 && (AD_MAX_CHUNKS - st->ad_nded) * st->ad_stride <= ops;
         st->smem_adam_big = ops + st->ad_nded * st->ad_stride + 1024;
         if (const char* v = getenv("DEEPIMPUTE_B200_ADAM")) if (!strcmp(v, "ring")) st->adam_big = false;
+        if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_GROUPS")) st->ad_groups = std::max(1, std::min(AD_MAX_GROUPS, atoi(v)));
     }
     if (st->smem_adam > 227 * 1024 || !st->fwd1_train[0].stages || !st->fwd2_train[0].stages || !st->bwd_train[0].stages ||
         !st->fwd1_train[1].stages || !st->fwd2_train[1].stages || !st->bwd_train[1].stages || !st->infer.stages) {
@@ -1141,8 +1165,9 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam");
     q.ad_nded = st->ad_nded; q.ad_stride = st->ad_stride;
     if (st->adam_big) {
-        if (st->x3) tc_adam_big_kernel<true><<<grid, NTHREADS_BIG, st->smem_adam_big, pl.main>>>(m1, m2, q);
-        else tc_adam_big_kernel<false><<<grid, NTHREADS_BIG, st->smem_adam_big, pl.main>>>(m1, m2, q);
+        const int nthreads = (4 * st->ad_groups + 2) * 32;
+        if (st->x3) tc_adam_big_kernel<true><<<grid, nthreads, st->smem_adam_big, pl.main>>>(m1, m2, q);
+        else tc_adam_big_kernel<false><<<grid, nthreads, st->smem_adam_big, pl.main>>>(m1, m2, q);
     } else if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, pl.main>>>(m1, m2, q);
     else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, pl.main>>>(m1, m2, q);
     if (t) { delete t; count_launch(e, "adam"); }

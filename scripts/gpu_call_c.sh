@@ -25,6 +25,6 @@ for d in 1; do
 done
 DEEPIMPUTE_B200_GRAPH=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_adam_kernel -s 40 -c 1 -o $out/full_c3_adam \
     python bench.py --steps 1 --warmup 0 --epochs 1 --no-cpu-baseline > $out/full_c3.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'impute_kernel|counts_to_norm' -c 3 -o $out/full_impute \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'impute_kernel|counts_to_norm' -c 3 -o $out/full_post_impute \
     python scripts/trace_step.py impute > $out/full_impute.log 2>&1
 tail -n 8 $out/pytest_gpu.txt; cat $out/ab.txt; tail -n 3 $out/ab_*.err | tail -n 20; tail -n 3 $out/full_c3.log $out/full_impute.log; ls -la $out

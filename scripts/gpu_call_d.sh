@@ -23,6 +23,6 @@ DEEPIMPUTE_B200_TRACE=1 DEEPIMPUTE_B200_DEEP=1 timeout 120 python scripts/trace_
 timeout 120 deepimpute_b200/csrc/umma_bench > $out/umma_bench.txt 2>&1
 DEEPIMPUTE_B200_GRAPH=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_adam -s 40 -c 1 -o $out/full_c3_adam \
     python bench.py --steps 1 --warmup 0 --epochs 1 --no-cpu-baseline > $out/full_c3.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'impute_kernel|counts_to_norm' -c 3 -o $out/full_impute \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'impute_kernel|counts_to_norm' -c 3 -o $out/full_post_impute \
     python scripts/trace_step.py impute > $out/full_impute.log 2>&1
 tail -n 8 $out/pytest_gpu.txt; cat $out/ab.txt; cat $out/umma_bench.txt; grep -A22 "trace adam" $out/trace_x3_big.txt | tail -n 24; tail -n 2 $out/full_c3.log | cut -c1-200; ls -la $out
