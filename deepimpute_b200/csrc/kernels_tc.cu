@@ -294,6 +294,20 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
         const int ncol = p.n_cols;
         const int c_lo = (X3 && upper) ? ncol / 2 : 0;
         const int c_hi = (X3 && !upper) ? ncol / 2 : ncol;
+        // global operands of the epilogue are fetched now, a whole main loop before they are needed: bias, the Adam
+        // state of the bias this thread will update, the per-epoch tables of the epoch graph
+        const int64_t bias_i = (int64_t)s * ((OP == TC_FWD2) ? p.Op : p.Hp) + f;
+        float bias = 0.f, bw = 0.f, bm = 0.f, bv = 0.f;
+        if (f_ok) {
+            if constexpr (OP == TC_FWD1) bias = p.b1[bias_i];
+            if constexpr (OP == TC_FWD2) bias = p.b2[bias_i];
+            if (p.training && !upper) {
+                if constexpr (OP == TC_FWD2) { bw = bias; bm = p.mb2[bias_i]; bv = p.vb2[bias_i]; }
+                if constexpr (OP == TC_BWD) { bw = p.b1[bias_i]; bm = p.mb1[bias_i]; bv = p.vb1[bias_i]; }
+            }
+        }
+        const AdamParams adam_b = adam_of(p);
+        const uint32_t dstep = (OP == TC_FWD1) ? dropout_step(p) : 0u;
         if constexpr (X3) convert(upper ? (warp - 2) * 32 + lane : warp * 32 + lane);
         if (p.aux_cols > 0) mbar_wait(&aux_bar, 0, 5);
         DI_TRACE_T0(2);
@@ -302,9 +316,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
         DI_TRACE_T0(3);
 
         if constexpr (OP == TC_FWD1) {
-            const float bias = f_ok ? p.b1[(int64_t)s * p.Hp + f] : 0.f;
             const bool drop = p.training && p.drop_thresh;
-            const uint32_t dstep = dropout_step(p);
             float* hrow = p.Hact + row0 * p.ldh + (int64_t)s * p.Hp + f;
             float* hlo = (p.training && p.Hlo) ? p.Hlo + (int64_t)s * p.Hp + f : nullptr;   // training h starts at row 0
             for (int c = c_lo; c < c_hi; c += 16) {
@@ -335,8 +347,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                 }
             }
         } else if constexpr (OP == TC_FWD2) {
-            const int64_t bi = (int64_t)s * p.Op + f;
-            const float bias = f_ok ? p.b2[bi] : 0.f;
+            const int64_t bi = bias_i;
             float part = 0.f, gsum = 0.f;
             const int rows_left = p.n_valid - row_tile * ncol;
             for (int c = c_lo; c < c_hi; c += 16) {
@@ -390,7 +401,10 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                 named_bar_sync(1, X3 ? 256 : 128);
                 if (!upper) {
                     if constexpr (X3) gsum += gpart[fl];
-                    if (p.training && f_ok) adam_update_fast(gsum, p.b2[bi], p.mb2[bi], p.vb2[bi], adam_of(p));
+                    if (p.training && f_ok) {
+                        adam_update_fast(gsum, bw, bm, bv, adam_b);
+                        p.b2[bi] = bw; p.mb2[bi] = bm; p.vb2[bi] = bv;
+                    }
                     if (p.loss && threadIdx.x == 0) {
                         double tot = red[0] + red[1] + red[2] + red[3];
                         if constexpr (X3) tot += red[4] + red[5] + red[6] + red[7];
@@ -399,7 +413,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                 }
             }
         } else {
-            const int64_t bi = (int64_t)s * p.Hp + f;
+            const int64_t bi = bias_i;
             float gsum = 0.f;
             for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16], h[16];
@@ -431,7 +445,10 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                 named_bar_sync(1, 256);
                 if (!upper) gsum += gpart[fl];
             }
-            if (!upper && f_ok) adam_update_fast(gsum, p.b1[bi], p.mb1[bi], p.vb1[bi], adam_of(p));
+            if (!upper && f_ok) {
+                adam_update_fast(gsum, bw, bm, bv, adam_b);
+                p.b1[bi] = bw; p.mb1[bi] = bm; p.vb1[bi] = bv;
+            }
         }
     }
 
