@@ -62,6 +62,7 @@ struct TcParams {
     int lo_stages;              // X3: ring of residual (lo) slabs written by the converter warps
     int which;                  // ADAM: 1 = W1 (in = X, dout = dz1), 2 = W2 (in = h, dout = dz2)
     int nkb_adam;               // ADAM: K blocks = padded batch rows / 32
+    int ad_kg;                  // ADAM ring kernel: K blocks resident per pass (operand buffers hold ad_kg of them)
     int64_t row0;               // first row of the batch / cell tile group inside the B-operand tensor
     int64_t rows_per_block_y;   // inference: blockIdx.y / m_tiles selects a cell tile of n_cols rows
     int m_tiles;                // feature tiles per sub-network
@@ -491,15 +492,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t b_block_bytes = (uint32_t)p.n_cols * BLOCK_K * 4;
+    const int KG = p.ad_kg;                               // K blocks per pass
+    const int ppr = (nkb + KG - 1) / KG;                  // passes per compensation round
     uint8_t* sA = smem;
-    uint8_t* sB = smem + (size_t)nkb * A_STAGE_BYTES;
-    float* wring = reinterpret_cast<float*>(sB + (size_t)nkb * b_block_bytes);
+    uint8_t* sB = smem + (size_t)KG * A_STAGE_BYTES;
+    float* wring = reinterpret_cast<float*>(sB + (size_t)KG * b_block_bytes);
     const int wbox = second ? p.wbox2 : p.wbox;
     const int tile_floats = AD_R * wbox;                  // one tensor, one chunk
     const uint32_t chunk_bytes = 3u * tile_floats * 4u;
     // ring stages: AD_STAGES dedicated ones, then as many as fit in the operand buffers, which are dead once the
     // accumulator is complete -- the deeper ring is what keeps enough bytes in flight to cover HBM latency
-    const uint32_t ops_bytes = (uint32_t)nkb * (A_STAGE_BYTES + b_block_bytes);
+    const uint32_t ops_bytes = (uint32_t)KG * (A_STAGE_BYTES + b_block_bytes);
     const int ring = min(AD_MAX_RING, AD_STAGES + (int)(ops_bytes / chunk_bytes));
     auto stage_ptr = [&](int st) -> float* {
         return st < AD_STAGES ? wring + (size_t)st * 3 * tile_floats
@@ -534,26 +537,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     if (warp == 4) {
         // ===== TMA: operands, then the w/m/v ring (loads ahead of the epilogue, stores behind it) =====
         if (elect_one()) {
-            auto load_a = [&](const CUtensorMap* m) {
-                for (int kb = 0; kb < nkb; ++kb)
-                    load_stage<true>(sA + (size_t)kb * A_STAGE_BYTES, m, &ops_bar, a_c0, kb * BLOCK_K, TILE_M);
-            };
-            auto load_b = [&](const CUtensorMap* m) {
-                for (int kb = 0; kb < nkb; ++kb)
-                    load_stage<true>(sB + (size_t)kb * b_block_bytes, m, &ops_bar, b_c0, b_c1 + kb * BLOCK_K, p.n_cols);
-            };
-            // X3 rounds: dout_hi in_lo, dout_hi in_hi, dout_lo in_hi -- every operand is fetched exactly once and a
-            // round reloads only the buffer whose contents change (non-X3: Blo aliases B, one round)
-            mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * (A_STAGE_BYTES + b_block_bytes));
-            load_a(&mapA); load_b(&mapBlo);                        // round 0: dout_hi, in_lo
-            for (int c = 0; c < min(AD_STAGES, nchunks); ++c) load_chunk(c);
-            if constexpr (X3) {
-                mbar_wait(&mma_bar, 0, 9);                         // round 0 MMAs have read the buffers
-                mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * b_block_bytes);
-                load_b(&mapB);                                     // round 1: dout_hi (kept), in_hi
-                mbar_wait(&mma_bar, 1, 9);
-                mbar_arrive_expect_tx(&ops_bar, (uint32_t)nkb * A_STAGE_BYTES);
-                load_a(&mapAlo);                                   // round 2: dout_lo, in_hi (kept)
+            // passes: X3 rounds (dout_hi in_lo, dout_hi in_hi, dout_lo in_hi) x groups of KG K blocks; a pass reloads
+            // the operand buffers once the MMAs of the previous pass have read them (plain TF32: one round, Blo == B)
+            constexpr int ROUNDS = X3 ? 3 : 1;
+            for (int pi = 0; pi < ROUNDS * ppr; ++pi) {
+                const int round = pi / ppr, kb0 = (pi % ppr) * KG, cnt = min(KG, nkb - kb0);
+                if (pi > 0) mbar_wait(&mma_bar, (pi - 1) & 1, 9);
+                mbar_arrive_expect_tx(&ops_bar, (uint32_t)cnt * (A_STAGE_BYTES + b_block_bytes));
+                const CUtensorMap* ma = (round == 2) ? &mapAlo : &mapA;
+                const CUtensorMap* mb = (X3 && round == 0) ? &mapBlo : &mapB;
+                for (int k = 0; k < cnt; ++k) {
+                    load_stage<true>(sA + (size_t)k * A_STAGE_BYTES, ma, &ops_bar, a_c0, (kb0 + k) * BLOCK_K, TILE_M);
+                    load_stage<true>(sB + (size_t)k * b_block_bytes, mb, &ops_bar, b_c0, b_c1 + (kb0 + k) * BLOCK_K, p.n_cols);
+                }
+                if (pi == 0) for (int c = 0; c < min(AD_STAGES, nchunks); ++c) load_chunk(c);
             }
             if (ring > AD_STAGES) {                                // the operand buffers join the ring
                 mbar_wait(&tmem_full_bar, 0, 4);
@@ -591,17 +588,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
         if (elect_one()) {
             const uint32_t idesc = idesc_for(p.n_cols, true, true);
             constexpr int ROUNDS = X3 ? 3 : 1;
-            for (int round = 0; round < ROUNDS; ++round) {
-                mbar_wait(&ops_bar, round & 1, 6);
+            const int npass = ROUNDS * ppr;
+            for (int pi = 0; pi < npass; ++pi) {
+                const int cnt = min(KG, nkb - (pi % ppr) * KG);
+                mbar_wait(&ops_bar, pi & 1, 6);
                 tc_fence_after();
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const uint32_t sa = smem_u32(sA + (size_t)kb * A_STAGE_BYTES);
-                    const uint32_t sb = smem_u32(sB + (size_t)kb * b_block_bytes);
+                for (int k = 0; k < cnt; ++k) {
+                    const uint32_t sa = smem_u32(sA + (size_t)k * A_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(sB + (size_t)k * b_block_bytes);
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
-                        umma_tf32(tmem, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (round | kb | j) ? 1u : 0u);
+                        umma_tf32(tmem, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (pi | k | j) ? 1u : 0u);
                 }
-                if (round + 1 < ROUNDS) umma_commit(&mma_bar);
+                if (pi + 1 < npass) umma_commit(&mma_bar);
             }
             umma_commit(&tmem_full_bar);
         }
@@ -886,7 +885,7 @@ struct TcState {
     int aux_h = 0, aux_y = 0, wbox1 = 0, wbox2 = 0;
     bool adam_direct = true;                               // DEEPIMPUTE_B200_ADAM_STORE=tma selects the in-place ring + TMA stores
     bool adam_big = false;                                 // one-CTA-per-SM ADAM kernel (DEEPIMPUTE_B200_ADAM=ring disables it)
-    int smem_adam_big = 0, ad_nded = 0, ad_stride = 0, ad_groups = 4;
+    int smem_adam_big = 0, ad_nded = 0, ad_stride = 0, ad_groups = 4, ad_kg = 2;
 };
 
 void drop_epoch_graph(TcState* st) {
@@ -915,6 +914,7 @@ TcState::Cfg pick_cfg(int n_cols, int aux_floats, bool x3, bool deep = false, in
             if (bytes <= budget) { c.stages = hs; c.lo_stages = ls; c.smem = bytes; return c; }
         }
     }
+    if (aux_floats > 0) return pick_cfg(n_cols, 0, x3, deep, only_budget);   // large batches: side operand read from global
     return c;      // stages == 0: does not fit
 }
 
@@ -1034,7 +1034,8 @@ bool tc_init(Engine& e) {
     if (cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc((void**)&st->d_step_base, sizeof(uint32_t)) != cudaSuccess) { e.err = "epoch-graph set-up failed"; return false; }
     const int nkb = e.Bp / BLOCK_K;
-    st->smem_adam = nkb * (int)(A_STAGE_BYTES + ADAM_TILE * BLOCK_K * 4) + AD_STAGES * 3 * AD_R * TILE_M * 4 + 1024;
+    st->ad_kg = std::min(nkb, 2);         // ring kernel: two K blocks (64 KB of operands) per pass, two CTAs per SM
+    st->smem_adam = st->ad_kg * (int)(A_STAGE_BYTES + ADAM_TILE * BLOCK_K * 4) + AD_STAGES * 3 * AD_R * TILE_M * 4 + 1024;
     {   // one-CTA-per-SM variant: all operand sets resident + a stage per chunk
         const int nsets = st->x3 ? 4 : 2;
         const int ops = nsets * nkb * (int)A_STAGE_BYTES;
@@ -1180,7 +1181,7 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
         m2.Alo = st->DZ2lo_mn; m2.Blo = st->Hlo_mn;
     } else { m1.Alo = m1.A; m1.Blo = m1.B; m2.Alo = m2.A; m2.Blo = m2.B; }
     KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam");
-    q.ad_nded = st->ad_nded; q.ad_stride = st->ad_stride;
+    q.ad_nded = st->ad_nded; q.ad_stride = st->ad_stride; q.ad_kg = st->ad_kg;
     if (st->adam_big) {
         const int nthreads = (4 * st->ad_groups + 2) * 32;
         if (st->x3) tc_adam_big_kernel<true><<<grid, nthreads, st->smem_adam_big, pl.main>>>(m1, m2, q);

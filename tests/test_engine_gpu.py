@@ -70,6 +70,8 @@ SHAPES = [
     ([1], 8, 8, 4),                            # degenerate: one predictor
     ([600], 256, 512, 64),                     # default topology, one sub-network
     ([129, 2, 64, 31, 257], 300, 96, 32),      # O not a multiple of 32, H = 300 (deepImpute_test.py)
+    ([2048, 700], 256, 512, 256),              # BASELINE.json configs[4]: batch 256, predictors capped at 2048
+    ([540, 512], 256, 512, 128),               # batch 128: the weight-gradient operands take two passes
 ]
 
 
@@ -95,11 +97,12 @@ def test_forward_matches_oracle(mode, n_pred, H, O, B):
 @pytest.mark.parametrize("nrows", ["full", "partial"])
 def test_single_step_matches_oracle(mode, n_pred, H, O, B, nrows):
     """Loss, every intermediate (h, dz2, dz1), Adam first/second moments and the updated weights of one step."""
-    norm, pred_idx, targ_idx = make_problem(150, max(1200, sum(n_pred)), n_pred, O, seed=2)
+    n_cells = max(150, B + 22)
+    norm, pred_idx, targ_idx = make_problem(n_cells, max(1200, sum(n_pred)), n_pred, O, seed=2)
     eng, ref = pair(n_pred, H, O, B, mode)
     eng.set_data(norm, pred_idx, targ_idx)
     n = B if nrows == "full" else max(1, B - 5)
-    rows = np.random.default_rng(3).choice(150, n, replace=False).astype(np.int32)
+    rows = np.random.default_rng(3).choice(n_cells, n, replace=False).astype(np.int32)
     X, Y = stage(norm, pred_idx, targ_idx, rows)
     step = 4
     inter = [ref.gradients(s, X[s], Y[s], step)[2] for s in range(len(n_pred))]
@@ -171,6 +174,34 @@ def test_epochs_match_oracle(mode):
         assert val == pytest.approx(val_ref, rel=tol)
     assert eng.steps_done == step == 24
     want = np.hstack(ref.forward(stage(norm, pred_idx, targ_idx, np.arange(240))[0]))
+    assert rel_err(eng.predict(), want) < PRED_TOL[mode]
+    eng.close()
+
+
+@pytest.mark.parametrize("mode", modes())
+@pytest.mark.parametrize("B", [128, 256])
+def test_epochs_with_large_batches(mode, B):
+    """batch 128 / 256 (BASELINE.json configs[4] trains at 256): the epoch graph, N = 256 MMAs, the weight-gradient
+    GEMM in several K passes, partial last batch."""
+    n_pred, H, O = [96, 40, 130], 40, 64
+    n_cells = 3 * B + 57
+    norm, pred_idx, targ_idx = make_problem(n_cells, 900, n_pred, O, seed=15)
+    eng, ref = pair(n_pred, H, O, B, mode, lr=5e-4)
+    eng.set_data(norm, pred_idx, targ_idx)
+    cells = np.random.default_rng(2).permutation(n_cells)
+    test_rows, train_rows = cells[:20].astype(np.int32), np.sort(cells[20:]).astype(np.int32)
+    eng.set_split(train_rows, test_rows)
+    Xtr, Ytr = stage(norm, pred_idx, targ_idx, train_rows)
+    Xte, Yte = stage(norm, pred_idx, targ_idx, test_rows)
+    step = 0
+    for e in range(2):
+        perm = epoch_permutation(7, e, len(train_rows))
+        loss_ref, step = ref.train_epoch(Xtr, Ytr, perm, step)
+        loss, val = eng.train_epoch(perm)
+        assert loss == pytest.approx(loss_ref, rel=EPOCH_TOL[mode])
+        assert val == pytest.approx(ref.loss(Xte, Yte), rel=EPOCH_TOL[mode])
+    assert eng.steps_done == step == 8                      # 3 B + 37 training cells: three full batches and a partial one
+    want = np.hstack(ref.forward(stage(norm, pred_idx, targ_idx, np.arange(n_cells))[0]))
     assert rel_err(eng.predict(), want) < PRED_TOL[mode]
     eng.close()
 
