@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 #include "engine.h"
 #include "tc_common.cuh"
@@ -80,6 +81,9 @@ struct TcParams {
     float *W1, *mW1, *vW1, *W2, *mW2, *vW2;      // ADAM, direct mode: updated values go to global memory from registers
     int adam_direct;                             // 1: registers -> st.global; 0: in place in the ring + TMA stores
     int ad_nded, ad_stride;                      // one-CTA-per-SM ADAM kernel: dedicated chunk stages, bytes per stage
+    int pdl_early;                               // release the dependent grid right after this one's own wait (experiment)
+    int pdl_prefetch;                            // fetch what the previous grid does not write before waiting for it
+    int pdl_lead;                                // > 0: release the dependent grid this many K blocks before the main loop ends
     float* out; int64_t ld_out;                  // inference output
     double* loss;
     int n_valid;                                 // real rows of the batch / chunk
@@ -103,6 +107,13 @@ struct TcParams {
 // (a bare `if (threadIdx.x == 0)` in front of them left warp 0 diverged: launch failures and hung mbarriers).
 #define DI_TRACE(slot) do { if (p.trace && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x == 0) p.trace[(slot)] = clock64(); } while (0)
 #define DI_TRACE_T0(slot) do { if (p.trace && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x == 0) p.trace[(slot)] = clock64(); __syncwarp(); } while (0)
+
+// Programmatic dependent launch: the kernels of an optimiser step form a chain on one stream.  Every kernel waits here
+// (after its prologue: barriers, TMEM allocation) for the previous grid to complete and flush, and releases its own
+// dependents once its accumulator is complete, so that the next kernel's launch latency and prologue overlap this
+// kernel's epilogue.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t dropout_step(const TcParams& p) { return p.step_base ? *p.step_base + p.step : p.step; }
 __device__ __forceinline__ AdamParams adam_of(const TcParams& p) {
@@ -199,6 +210,9 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
+    // the producer warp waits for the previous grid later: the operand that grid does not write is fetched first
+    if (warp != 4) pdl_wait();
+    if (p.pdl_early && threadIdx.x == 0) pdl_release();
     DI_TRACE_T0(1);
 
     // residual pass (X3): lo = a - trunc19(a) for every float of the slab TMA just delivered, written to the next slab
@@ -234,20 +248,42 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
     if (warp == 4) {
         // ===== TMA producer =====
         if (elect_one()) {
-            for (int kb = 0; kb < nkb; ++kb) {
+            auto load_a = [&](int kb, int st) {
+                uint8_t* sa = smem + (size_t)st * stage_bytes;
+                if constexpr (A_MN) load_stage<true>(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K, TILE_M);
+                else tma_load_2d(sa, &mapA, &full_bar[st], a_c0 + kb * BLOCK_K, a_c1);
+            };
+            auto load_b = [&](int kb, int st) {
+                tma_load_2d(smem + (size_t)st * stage_bytes + A_STAGE_BYTES, &mapB, &full_bar[st], b_c0 + kb * BLOCK_K, b_c1);
+            };
+            auto load_aux = [&]() {                       // side operand of the epilogue, needed only after the MMAs
+                mbar_arrive_expect_tx(&aux_bar, (uint32_t)(p.n_cols * p.aux_cols * 4));
+                tma_load_2d((void*)aux, &mapC, &aux_bar, c_c0, (int32_t)p.aux_row0);
+            };
+            // What the grid ahead of this one in the step's chain does NOT write can be fetched before waiting for
+            // it: FWD1 follows ADAM (writes W1, not the staged batch X); FWD2 follows FWD1 (writes h, not W2 or the
+            // Y tile); BWD follows FWD2 (writes dz2, not W2 or the h tile).  Every earlier grid has completed by
+            // the time this one was released (the releasing grid had passed its own wait).
+            constexpr bool A_FIRST = (OP != TC_FWD1);
+            const int npre = p.pdl_prefetch ? min(stages, nkb) : 0;
+            for (int kb = 0; kb < npre; ++kb) {
+                mbar_arrive_expect_tx(&full_bar[kb], hi_bytes);
+                if (kb < 40) DI_TRACE(8 + kb);
+                if constexpr (A_FIRST) load_a(kb, kb); else load_b(kb, kb);
+            }
+            if (npre && p.aux_cols > 0) load_aux();
+            pdl_wait();
+            for (int kb = 0; kb < npre; ++kb) {
+                if constexpr (A_FIRST) load_b(kb, kb); else load_a(kb, kb);
+            }
+            for (int kb = npre; kb < nkb; ++kb) {
                 const int st = kb % stages;
                 if (kb >= stages) mbar_wait(&empty_bar[st], ((kb / stages) - 1) & 1, 2);
                 if (kb < 40) DI_TRACE(8 + kb);
-                uint8_t* sa = smem + (size_t)st * stage_bytes;
-                uint8_t* sb = sa + A_STAGE_BYTES;
                 mbar_arrive_expect_tx(&full_bar[st], hi_bytes);
-                if constexpr (A_MN) load_stage<true>(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K, TILE_M);
-                else tma_load_2d(sa, &mapA, &full_bar[st], a_c0 + kb * BLOCK_K, a_c1);
-                tma_load_2d(sb, &mapB, &full_bar[st], b_c0 + kb * BLOCK_K, b_c1);
-                if (kb == 0 && p.aux_cols > 0) {          // side operand of the epilogue, needed only after the MMAs
-                    mbar_arrive_expect_tx(&aux_bar, (uint32_t)(p.n_cols * p.aux_cols * 4));
-                    tma_load_2d((void*)aux, &mapC, &aux_bar, c_c0, (int32_t)p.aux_row0);
-                }
+                load_a(kb, st);
+                load_b(kb, st);
+                if (kb == 0 && p.aux_cols > 0) load_aux();
             }
         }
     } else if (warp == 5) {
@@ -279,6 +315,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                 }
                 umma_commit(&empty_bar[st]);
                 if constexpr (X3) umma_commit(&lo_free[ls]);
+                if (p.pdl_lead > 0 && kb == nkb - 1 - p.pdl_lead) pdl_release();
             }
             umma_commit(&tmem_full_bar);
         }
@@ -314,6 +351,8 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
         DI_TRACE_T0(2);
         mbar_wait(&tmem_full_bar, 0, 4);
         tc_fence_after();
+        if (threadIdx.x == 0) pdl_release();
+        __syncwarp();
         DI_TRACE_T0(3);
 
         if constexpr (OP == TC_FWD1) {
@@ -523,6 +562,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
+    pdl_wait();
+    if (p.pdl_early && threadIdx.x == 0) pdl_release();
+    __syncwarp();
 
     auto load_chunk = [&](int c) {                        // one elected thread
         const int st = c % ring;
@@ -612,6 +654,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
         DI_TRACE_T0(2);
         mbar_wait(&tmem_full_bar, 0, 4);
         tc_fence_after();
+        if (threadIdx.x == 0) pdl_release();
+        __syncwarp();
         DI_TRACE_T0(3);
         for (int c = 0; c < nchunks; ++c) {
             const int st = c % ring;
@@ -740,6 +784,9 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
+    if (warp != 4 * ngroups) pdl_wait();                   // the producer warp waits later (see below)
+    if (p.pdl_early && threadIdx.x == 0) pdl_release();
+    __syncwarp();
 
     if (warp == 4 * ngroups) {
         if (elect_one()) {
@@ -759,16 +806,35 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
                 tma_load_2d(ws + tile_floats, &mapM, &wfull[c], m0, r);
                 tma_load_2d(ws + 2 * tile_floats, &mapV, &wfull[c], m0, r);
             };
+            // ADAM follows BWD, which writes dz1 (the `dout` of the W1 tiles) and nothing else this kernel reads: the
+            // w / m / v chunks, the `in` operands and -- for W2 tiles -- dout = dz2 are fetched before waiting for it
+            const bool a_free = p.pdl_prefetch && second;
+            const bool early = p.pdl_prefetch != 0;
             if constexpr (X3) {
                 mbar_arrive_expect_tx(&ops_bar[0], 3u * set_bytes);
-                load_a(&mapA, set0, &ops_bar[0]); load_b(&mapBlo, set1, &ops_bar[0]); load_b(&mapB, set2, &ops_bar[0]);
                 mbar_arrive_expect_tx(&ops_bar[1], set_bytes);
-                load_a(&mapAlo, set3, &ops_bar[1]);
             } else {
                 mbar_arrive_expect_tx(&ops_bar[0], 2u * set_bytes);
-                load_a(&mapA, set0, &ops_bar[0]); load_b(&mapB, set1, &ops_bar[0]);
             }
-            for (int c = 0; c < min(p.ad_nded, nchunks); ++c) load_chunk(c);
+            auto load_in = [&]() {
+                if constexpr (X3) { load_b(&mapBlo, set1, &ops_bar[0]); load_b(&mapB, set2, &ops_bar[0]); }
+                else load_b(&mapB, set1, &ops_bar[0]);
+            };
+            auto load_dout = [&]() {
+                load_a(&mapA, set0, &ops_bar[0]);
+                if constexpr (X3) load_a(&mapAlo, set3, &ops_bar[1]);
+            };
+            if (early) {
+                load_in();
+                if (a_free) load_dout();
+                for (int c = 0; c < min(p.ad_nded, nchunks); ++c) load_chunk(c);
+                pdl_wait();
+                if (!a_free) load_dout();
+            } else {
+                pdl_wait();
+                load_dout(); load_in();
+                for (int c = 0; c < min(p.ad_nded, nchunks); ++c) load_chunk(c);
+            }
             if (nchunks > p.ad_nded) {                             // the operand area becomes chunk stages
                 mbar_wait(&tmem_full_bar, 0, 4);
                 for (int c = p.ad_nded; c < nchunks; ++c) load_chunk(c);
@@ -807,6 +873,8 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
         DI_TRACE_T0(2);
         mbar_wait(&tmem_full_bar, 0, 4);
         tc_fence_after();
+        if (threadIdx.x == 0) pdl_release();
+        __syncwarp();
         DI_TRACE_T0(3);
         float* gw0 = second ? p.W2 : p.W1;
         float* gm0 = second ? p.mW2 : p.mW1;
@@ -885,6 +953,10 @@ struct TcState {
     int aux_h = 0, aux_y = 0, wbox1 = 0, wbox2 = 0;
     bool adam_direct = true;                               // DEEPIMPUTE_B200_ADAM_STORE=tma selects the in-place ring + TMA stores
     bool adam_big = false;                                 // one-CTA-per-SM ADAM kernel (DEEPIMPUTE_B200_ADAM=ring disables it)
+    bool pdl = true;                                       // programmatic dependent launch along a step's kernel chain (DEEPIMPUTE_B200_PDL=0 disables)
+    bool pdl_early = false;                                // DEEPIMPUTE_B200_PDL=2: dependents released before the main loop instead of after it
+    bool pdl_prefetch = true;                              // DEEPIMPUTE_B200_PDL_PREFETCH=0: wait for the previous grid before any load
+    int pdl_lead = 0;                                      // DEEPIMPUTE_B200_PDL_LEAD=k: release dependents k K blocks before the main loop ends
     int smem_adam_big = 0, ad_nded = 0, ad_stride = 0, ad_groups = 4, ad_kg = 2;
 };
 
@@ -927,6 +999,18 @@ TcParams base_params(Engine& e) {
     p.drop_thresh = r > 0.0 ? (uint32_t)(r * 4294967296.0) : 0u;
     p.keep_scale = 1.0f;
     return p;
+}
+
+// kernel launch with or without the programmatic-stream-serialization attribute (see pdl_wait)
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kernel)(KArgs...), dim3 grid, int threads, int smem, cudaStream_t stream, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 template <int OP, bool X3>
@@ -995,6 +1079,9 @@ bool tc_init(Engine& e) {
     st->x3_bwd = st->x3;
     if (const char* v = getenv("DEEPIMPUTE_B200_EXPERIMENT")) st->simt_adam = atoi(v) & 2;
     if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_STORE")) st->adam_direct = strcmp(v, "tma") != 0;
+    if (const char* v = getenv("DEEPIMPUTE_B200_PDL")) { st->pdl = atoi(v) != 0; st->pdl_early = atoi(v) == 2; }
+    if (const char* v = getenv("DEEPIMPUTE_B200_PDL_PREFETCH")) st->pdl_prefetch = atoi(v) != 0;
+    if (const char* v = getenv("DEEPIMPUTE_B200_PDL_LEAD")) st->pdl_lead = std::max(0, atoi(v));
     for (int deep = 0; deep < 2; ++deep) {
         st->fwd1_train[deep] = pick_cfg(e.Bp, 0, st->x3, deep);
         st->fwd2_train[deep] = pick_cfg(e.Bp, (st->x3 && !deep) ? 0 : aux_floats, st->x3, deep);
@@ -1122,9 +1209,10 @@ struct StepPlan {
 template <int OP, bool X3>
 void launch_on(Engine& e, const StepPlan& pl, const char* name, const CUtensorMap& a, const CUtensorMap& b,
                const CUtensorMap& c, const TcParams& p, dim3 grid, int smem) {
-    if (pl.graph) { tc_kernel<OP, X3><<<grid, X3 ? NTHREADS_X3 : NTHREADS, smem, pl.main>>>(a, b, c, p); return; }
+    const bool pdl = static_cast<TcState*>(e.tc)->pdl;
+    if (pl.graph) { launch_k(tc_kernel<OP, X3>, grid, X3 ? NTHREADS_X3 : NTHREADS, smem, pl.main, pdl, a, b, c, p); return; }
     KernelTimer t(e, name);
-    tc_kernel<OP, X3><<<grid, X3 ? NTHREADS_X3 : NTHREADS, smem, pl.main>>>(a, b, c, p);
+    launch_k(tc_kernel<OP, X3>, grid, X3 ? NTHREADS_X3 : NTHREADS, smem, pl.main, false, a, b, c, p);
     count_launch(e, name);
 }
 
@@ -1142,6 +1230,9 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     p.inv_norm = 1.0f / ((float)a.n_valid * (float)e.O);
     p.loss = e.d_loss; p.adam = a.adam;
     p.s_base = pl.s0;
+    p.pdl_early = (st->pdl_early && pl.graph) ? 1 : 0;
+    p.pdl_prefetch = st->pdl_prefetch ? 1 : 0;
+    p.pdl_lead = (st->pdl && pl.graph) ? st->pdl_lead : 0;
     if (pl.graph) { p.step_base = st->d_step_base; p.lr_table = st->d_lr_table; }
     const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
     const TcState::Cfg& c1 = st->fwd1_train[pl.deep];
@@ -1184,10 +1275,11 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     q.ad_nded = st->ad_nded; q.ad_stride = st->ad_stride; q.ad_kg = st->ad_kg;
     if (st->adam_big) {
         const int nthreads = (4 * st->ad_groups + 2) * 32;
-        if (st->x3) tc_adam_big_kernel<true><<<grid, nthreads, st->smem_adam_big, pl.main>>>(m1, m2, q);
-        else tc_adam_big_kernel<false><<<grid, nthreads, st->smem_adam_big, pl.main>>>(m1, m2, q);
-    } else if (st->x3) tc_adam_kernel<true><<<grid, NTHREADS, st->smem_adam, pl.main>>>(m1, m2, q);
-    else tc_adam_kernel<false><<<grid, NTHREADS, st->smem_adam, pl.main>>>(m1, m2, q);
+        const bool pdl = st->pdl && pl.graph;
+        if (st->x3) launch_k(tc_adam_big_kernel<true>, grid, nthreads, st->smem_adam_big, pl.main, pdl, m1, m2, q);
+        else launch_k(tc_adam_big_kernel<false>, grid, nthreads, st->smem_adam_big, pl.main, pdl, m1, m2, q);
+    } else if (st->x3) launch_k(tc_adam_kernel<true>, grid, NTHREADS, st->smem_adam, pl.main, st->pdl && pl.graph, m1, m2, q);
+    else launch_k(tc_adam_kernel<false>, grid, NTHREADS, st->smem_adam, pl.main, st->pdl && pl.graph, m1, m2, q);
     if (t) { delete t; count_launch(e, "adam"); }
 }
 
