@@ -323,6 +323,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference)")
     from deepimpute_b200 import parallel
     from deepimpute_b200.engine import DEFAULT_MATH, Engine, epoch_permutation
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line (NCCL's version banner)
     ctx = parallel.init()
     torch.cuda.set_device(local)
     wl = build_workload(args.workload, "cuda:{}".format(local))

@@ -81,6 +81,7 @@ struct TcParams {
     float *W1, *mW1, *vW1, *W2, *mW2, *vW2;      // ADAM, direct mode: updated values go to global memory from registers
     int adam_direct;                             // 1: registers -> st.global; 0: in place in the ring + TMA stores
     int ad_nded, ad_stride;                      // one-CTA-per-SM ADAM kernel: dedicated chunk stages, bytes per stage
+    int ad_generic;                              // experiment: run-time pitches in the ADAM chunk update
     int pdl_early;                               // release the dependent grid right after this one's own wait (experiment)
     int pdl_prefetch;                            // fetch what the previous grid does not write before waiting for it
     int pdl_lead;                                // > 0: release the dependent grid this many K blocks before the main loop ends
@@ -718,6 +719,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
     DI_TRACE_T0(5);
 }
 
+// One [AD_R rows] x {w, m, v} chunk of one feature: shared memory -> registers -> Adam -> global memory.
+// WBOX / LD > 0: row pitch of the shared tile (floats) and of the weight matrix known at compile time.
+template <int WBOX, int LD>
+__device__ __forceinline__ void adam_chunk(uint32_t base, const float (&g)[AD_R], const AdamParams& adam,
+                                           float* __restrict__ gw, float* __restrict__ gm, float* __restrict__ gv,
+                                           int wbox_rt, int ld_rt) {
+    const uint32_t row_b = (WBOX > 0 ? (uint32_t)WBOX : (uint32_t)wbox_rt) * 4u;
+    const uint32_t tile_b = row_b * AD_R;
+    const int64_t ld = LD > 0 ? (int64_t)LD : (int64_t)ld_rt;
+    float w[AD_R], m[AD_R], v[AD_R];
+#pragma unroll
+    for (int r = 0; r < AD_R; ++r) {
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[r]) : "r"(base + r * row_b));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m[r]) : "r"(base + tile_b + r * row_b));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[r]) : "r"(base + 2 * tile_b + r * row_b));
+    }
+#pragma unroll
+    for (int r = 0; r < AD_R; ++r) adam_update_fast(g[r], w[r], m[r], v[r], adam);
+#pragma unroll
+    for (int r = 0; r < AD_R; ++r) {
+        gw[r * ld] = w[r];
+        gm[r * ld] = m[r];
+        gv[r * ld] = v[r];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ ADAM, one CTA per SM
 // Same tile and arithmetic as tc_adam_kernel, laid out for ONE resident CTA per SM that never waits on a buffer:
 //   * every operand set is resident at once (X3: dout_hi, in_lo, in_hi, dout_lo), so the three compensation rounds
@@ -888,23 +915,14 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
             __syncwarp();
             if (f_ok) {
                 const uint32_t base = smem_u32(stage_ptr(c)) + (uint32_t)fl * 4u;
-                const uint32_t row_b = (uint32_t)wbox * 4u, tile_b = (uint32_t)tile_floats * 4u;
-                float w[AD_R], m[AD_R], v[AD_R];
-#pragma unroll
-                for (int r = 0; r < AD_R; ++r) {
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[r]) : "r"(base + r * row_b));
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m[r]) : "r"(base + tile_b + r * row_b));
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[r]) : "r"(base + 2 * tile_b + r * row_b));
-                }
-#pragma unroll
-                for (int r = 0; r < AD_R; ++r) adam_update_fast(g[r], w[r], m[r], v[r], adam);
                 const int64_t off = (row_base + n0 + (int64_t)c * AD_R) * out_dim + m0 + fl;
-#pragma unroll
-                for (int r = 0; r < AD_R; ++r) {
-                    gw0[off + (int64_t)r * out_dim] = w[r];
-                    gm0[off + (int64_t)r * out_dim] = m[r];
-                    gv0[off + (int64_t)r * out_dim] = v[r];
-                }
+                // the epilogue is instruction-bound: with the row pitch known at compile time (the default topology:
+                // 128-wide tiles of W1 [.., 256] and W2 [.., 512]) every shared load and global store addresses
+                // base + immediate instead of computing 48 addresses per chunk
+                if (p.ad_generic) adam_chunk<0, 0>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, wbox, out_dim);
+                else if (wbox == TILE_M && out_dim == 256) adam_chunk<TILE_M, 256>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, 0, 0);
+                else if (wbox == TILE_M && out_dim == 512) adam_chunk<TILE_M, 512>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, 0, 0);
+                else adam_chunk<0, 0>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, wbox, out_dim);
             }
             if (tracer && c < 40) p.trace[48 + c] = clock64();
         }
@@ -1273,6 +1291,7 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     } else { m1.Alo = m1.A; m1.Blo = m1.B; m2.Alo = m2.A; m2.Blo = m2.B; }
     KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam");
     q.ad_nded = st->ad_nded; q.ad_stride = st->ad_stride; q.ad_kg = st->ad_kg;
+    { static const bool generic = [] { const char* v = getenv("DEEPIMPUTE_B200_ADAM_GENERIC"); return v && atoi(v) != 0; }(); q.ad_generic = generic ? 1 : 0; }
     if (st->adam_big) {
         const int nthreads = (4 * st->ad_groups + 2) * 32;
         const bool pdl = st->pdl && pl.graph;
