@@ -553,7 +553,6 @@ int di_train_epoch(di_handle* h, const int32_t* perm, int64_t first_step, float*
     if (!perm || first_step < 0) return fail(e, DI_ERR_ARG, "di_train_epoch: bad arguments");
     for (int64_t i = 0; i < e.n_train; ++i) if (perm[i] < 0 || perm[i] >= e.n_train) return fail(e, DI_ERR_ARG, "di_train_epoch: perm out of range");
     DI_CUDA(cudaSetDevice(e.cfg.device));
-    const int64_t ldy = (int64_t)e.S * e.Op;
     DI_CUDA(cudaMemcpyAsync(e.d_perm, perm, e.n_train * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
     DI_CUDA(cudaEventRecord(e.ev0, e.stream));
     DI_CUDA(cudaMemsetAsync(e.d_loss, 0, 2 * sizeof(double), e.stream));

@@ -221,9 +221,10 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
     auto convert = [&](int cid) {
         const int per_thread = (int)(hi_bytes / 16) / NCONV;          // float4 per thread; hi_bytes is a multiple of 4 KB
         for (int kb = 0; kb < nkb; ++kb) {
-            const int st = kb % stages, ls = kb % lo_stages;
+            const int lstages = X3 ? lo_stages : 1;       // (plain TF32 never instantiates a call of this lambda)
+            const int st = kb % stages, ls = kb % lstages;
             mbar_wait(&full_bar[st], (kb / stages) & 1, 1);
-            if (kb >= lo_stages) mbar_wait(&lo_free[ls], ((kb / lo_stages) - 1) & 1, 11);
+            if (kb >= lstages) mbar_wait(&lo_free[ls], ((kb / lstages) - 1) & 1, 11);
             const uint32_t hi = smem_u32(smem + (size_t)st * stage_bytes) + cid * 16;
             const uint32_t lo = smem_u32(lo_base + (size_t)ls * stage_bytes) + cid * 16;
             for (int i0 = 0; i0 < per_thread; i0 += 4) {
@@ -1236,7 +1237,6 @@ void launch_on(Engine& e, const StepPlan& pl, const char* name, const CUtensorMa
 
 void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const StepPlan& pl) {
     const CUtensorMap& Xk = which_x == 0 ? st->Xtr_k : st->Xstep_k;
-    const CUtensorMap& Xmn = which_x == 0 ? st->Xtr_mn : st->Xstep_mn;
     const CUtensorMap& Yaux = which_x == 0 ? st->Ytr_aux : st->Ystep_aux;
     TcParams p = base_params(e);
     p.n_cols = e.Bp; p.tmem_cols = pow2_cols(e.Bp);

@@ -1,6 +1,8 @@
 #!/bin/bash
-# Full evidence run: GPU tests, bench (both arms), launch list + full captures for profiles/.
-tag=${1:-s3f}
+# Full evidence run (one gpurun call): GPU tests, smoke, bench (both arms, c3 and c2), ncu launch list + full captures of the
+# ADAM, element-wise and inference kernels, pipeline trace.  usage: bash scripts/gpu_evidence.sh <tag>; then
+# python scripts/summarise_profile.py gpurun_out/<tag> <round-tag>
+tag=${1:-evidence}
 out=gpurun_out/$tag; mkdir -p $out
 timeout 900 python -m pytest tests -m gpu -q --durations=5 > $out/pytest_gpu.txt 2>&1; echo "pytest exit $?" >> $out/pytest_gpu.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.txt 2>&1; echo "smoke exit $?" >> $out/smoke.txt

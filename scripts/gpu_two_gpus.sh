@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2 GPUs: sharded MultiNet against the single-GPU one, and the bench line the driver would ask for at N=2.
-tag=${1:-s3h}
+tag=${1:-two_gpus}
 out=gpurun_out/$tag; mkdir -p $out
 nvidia-smi --query-gpu=index,name --format=csv > $out/gpus.txt 2>&1
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
