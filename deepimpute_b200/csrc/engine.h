@@ -74,7 +74,8 @@ struct Engine {
     // written by the epilogue (h, dz2, dz1) or the staging gather (X) that produces the value itself
     float *Hlo = nullptr, *DZ2lo = nullptr, *DZ1lo = nullptr, *Xtr_lo = nullptr, *Xstep_lo = nullptr;
 
-    int64_t chunk_rows = 0;                       // inference chunk (multiple of 128)
+    int infer_tile = 128;                         // cells per CTA of the inference forward (UMMA N): 128 or 256
+    int64_t chunk_rows = 0;                       // inference chunk (multiple of infer_tile)
     float *Xchunk = nullptr, *Hchunk = nullptr, *Ochunk = nullptr, *OchunkB = nullptr;
     float* Ochunk2[2] = {nullptr, nullptr};       // {Ochunk, OchunkB}: double buffer of the direct D2H path
     cudaEvent_t ev_fwd[2] = {nullptr, nullptr};

@@ -48,7 +48,7 @@ constexpr int NCONV = 256;           // converter threads of an X3 CTA
 constexpr int MAX_STAGES = 6;
 constexpr uint32_t A_STAGE_BYTES = TILE_M * BLOCK_K * 4;       // 16 KB
 
-constexpr int INFER_TILE = 128;      // cells per CTA at inference (UMMA N)
+// cells per CTA at inference (UMMA N): Engine::infer_tile, 128 or 256
 constexpr int ADAM_TILE = 128;       // input features per CTA in the weight-gradient kernel (UMMA N)
 constexpr int AD_R = 8;              // weight rows per streamed chunk
 constexpr int AD_STAGES = 3;         // chunks of w/m/v in the dedicated part of the shared-memory ring
@@ -1082,8 +1082,8 @@ bool tc_init(Engine& e) {
         ok = ok && make_map_2d(&st->DZ1lo_mn, e.DZ1lo, e.Bp, SH, SH, 32, true);
         ok = ok && make_map_2d(&st->Xstep_lo_mn, e.Xstep_lo, e.Bp, e.PT, e.PT, 32, true);
     }
-    ok = ok && make_map_2d(&st->Xchunk_k, e.Xchunk, e.chunk_rows, e.PT, e.PT, INFER_TILE);
-    ok = ok && make_map_2d(&st->Hchunk_k, e.Hchunk, e.chunk_rows, SH, SH, INFER_TILE);
+    ok = ok && make_map_2d(&st->Xchunk_k, e.Xchunk, e.chunk_rows, e.PT, e.PT, e.infer_tile);
+    ok = ok && make_map_2d(&st->Hchunk_k, e.Hchunk, e.chunk_rows, SH, SH, e.infer_tile);
     float* w1[3] = {e.W1, e.mW1, e.vW1};
     float* w2[3] = {e.W2, e.mW2, e.vW2};
     for (int i = 0; i < 3; ++i) {
@@ -1116,7 +1116,7 @@ bool tc_init(Engine& e) {
         st->bwd_train[2] = pick_cfg(e.Bp, 0, st->x3, false, room);
         if (!st->fwd1_train[2].stages) { st->fwd1_train[2] = st->fwd1_train[0]; st->fwd2_train[2] = st->fwd2_train[0]; st->bwd_train[2] = st->bwd_train[0]; }
     }
-    st->infer = pick_cfg(INFER_TILE, 0, st->x3, true);
+    st->infer = pick_cfg(e.infer_tile, 0, st->x3, true);
     // sub-network groups of the epoch graph: independent chains on their own streams
     int G = std::min(16, e.S);
     if (const char* v = getenv("DEEPIMPUTE_B200_GROUPS")) G = std::max(1, std::min(std::min((int)TcState::MAX_GROUPS, e.S), atoi(v)));
@@ -1205,7 +1205,7 @@ bool tc_rebind(Engine& e) {
     ok = ok && make_map_2d(&st->Xtr_mn, e.Xtr, e.n_train_pad, e.PT, e.PT, 32, true);
     if (e.Xtr_lo) ok = ok && make_map_2d(&st->Xtr_lo_mn, e.Xtr_lo, e.n_train_pad, e.PT, e.PT, 32, true);
     ok = ok && make_map_plain(&st->Ytr_aux, e.Ytr, e.n_train_pad, SO, SO, st->aux_y, e.Bp);
-    ok = ok && make_map_2d(&st->Xte_k, e.Xte, e.n_test_pad, e.PT, e.PT, INFER_TILE);
+    ok = ok && make_map_2d(&st->Xte_k, e.Xte, e.n_test_pad, e.PT, e.PT, e.infer_tile);
     st->have_split = ok;
     drop_epoch_graph(st);             // the graph's nodes hold the old tensor maps
     st->graph_failed = false;
@@ -1409,11 +1409,11 @@ void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_va
     auto* st = static_cast<TcState*>(e.tc);
     const CUtensorMap& Xk = which_x == 2 ? st->Xte_k : st->Xchunk_k;
     TcParams p = base_params(e);
-    p.n_cols = INFER_TILE; p.tmem_cols = INFER_TILE; p.stages = st->infer.stages; p.lo_stages = st->infer.lo_stages;
-    p.rows_per_block_y = INFER_TILE;
+    p.n_cols = e.infer_tile; p.tmem_cols = e.infer_tile; p.stages = st->infer.stages; p.lo_stages = st->infer.lo_stages;
+    p.rows_per_block_y = e.infer_tile;
     p.ldh = (int64_t)e.S * e.Hp;
     p.n_valid = (int)n_valid; p.training = 0; p.drop_thresh = 0;
-    const int row_tiles = (int)(rows / INFER_TILE);
+    const int row_tiles = (int)(rows / e.infer_tile);
     const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
     // hidden activations of this pass live in Hchunk rows [0, rows)
     { TcParams q = p; q.m_tiles = mh; q.row0 = row0; q.Hact = e.Hchunk - row0 * q.ldh;
