@@ -81,6 +81,7 @@ struct TcParams {
     float *W1, *mW1, *vW1, *W2, *mW2, *vW2;      // ADAM, direct mode: updated values go to global memory from registers
     int adam_direct;                             // 1: registers -> st.global; 0: in place in the ring + TMA stores
     int ad_nded, ad_stride;                      // one-CTA-per-SM ADAM kernel: dedicated chunk stages, bytes per stage
+    int ts_wbox, ts_acol0;                       // TS kernels: features per row of the plain weight tile; first TMEM column of the weight slabs
     int ad_generic;                              // experiment: run-time pitches in the ADAM chunk update
     int pdl_early;                               // release the dependent grid right after this one's own wait (experiment)
     int pdl_prefetch;                            // fetch what the previous grid does not write before waiting for it
@@ -142,13 +143,40 @@ __device__ __forceinline__ void softplus_sigmoid(float z, float& sp, float& sg) 
     sg = (z >= 0.f) ? r : e * r;
 }
 
+// ---- A operand in tensor memory (verified bit-exact by csrc/umma_probe_ts.cu: lane = row m, one 32-bit column per k,
+// K step j of a slab reads columns [col0 + 8 j, col0 + 8 j + 8), a_major bit 0) --------------------------------------
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane (warp w writes lanes 32*(w%4) .. +31)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr),
+          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+constexpr int TS_COLS = 2 * BLOCK_K;     // TMEM columns of one weight slab: 32 of W (the tensor core truncates) + 32 of W_lo
+
 // ============================================================================================ FWD1 / FWD2 / BWD
 // X3 = error-compensated "3xTF32" products for the forward GEMMs: the tensor core truncates an fp32 operand a to
 // its upper 19 bits (a_hi); the epilogue warps, idle during the main loop, write the residual a_lo = a - a_hi of
 // every staged slab next to it (element-wise, so the swizzled layout carries over unchanged) and the MMA warp issues
 // a_lo*b_hi + a_hi*b_lo + a_hi*b_hi into the same accumulator.  The dropped a_lo*b_lo term is 2^-20 relative, i.e.
 // fp32-level products on the tensor cores, at 3x the (negligible) MMA time and 2x the staging memory.
-template <int OP, bool X3>
+// TS (X3 FWD1 / FWD2 only): the weight slab never becomes an MMA operand in shared memory.  TMA delivers it as a plain
+// [32 k][128 features] tile, the converter warps move it into tensor memory (W and W_lo side by side, tcgen05.st) and
+// the MMAs take A from there: per K block the tensor core then reads 24 KB of shared memory (the activation slabs)
+// instead of 72 KB, and the converters write 8 KB instead of 24 KB.
+template <int OP, bool X3, bool TS = false>
 __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                   const __grid_constant__ CUtensorMap mapB,
                                                                   const __grid_constant__ CUtensorMap mapC, const TcParams p) {
@@ -183,13 +211,15 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t b_stage_bytes = (uint32_t)p.n_cols * BLOCK_K * 4;
-    const uint32_t hi_bytes = A_STAGE_BYTES + b_stage_bytes;           // one slab: [A | B], what TMA writes per K block
-    const uint32_t stage_bytes = hi_bytes;
+    // one slab: [A | B], what TMA writes per K block (TS: the A part is a plain [32][ts_wbox] tile)
+    const uint32_t hi_bytes = (TS ? (uint32_t)(BLOCK_K * p.ts_wbox * 4) : A_STAGE_BYTES) + b_stage_bytes;
+    const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+    const uint32_t lo_stage_bytes = TS ? b_stage_bytes : stage_bytes;  // TS: only the activation slab has a residual in smem
     const int stages = p.stages;
     const int lo_stages = X3 ? p.lo_stages : 0;
     // shared memory: [raw ring: stages slabs][X3: residual ring: lo_stages slabs][aux tile]
     uint8_t* lo_base = smem + (size_t)stages * stage_bytes;
-    const float* aux = reinterpret_cast<const float*>(lo_base + (size_t)lo_stages * stage_bytes);
+    const float* aux = reinterpret_cast<const float*>(lo_base + (size_t)lo_stages * lo_stage_bytes);
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], lo_ready[MAX_STAGES], lo_free[MAX_STAGES], tmem_full_bar, aux_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ double red[8];
@@ -225,6 +255,38 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
             const int st = kb % stages, ls = kb % lstages;
             mbar_wait(&full_bar[st], (kb / stages) & 1, 1);
             if (kb >= lstages) mbar_wait(&lo_free[ls], ((kb / lstages) - 1) & 1, 11);
+            if constexpr (TS) {
+                // weights: this thread owns feature `quad * 32 + lane` (the TMEM lane its warp may write) and half of the
+                // slab's 32 k; W and its residual go to tensor memory, columns [ls * 64, +32) and [ls * 64 + 32, +32)
+                const int hw = (int)(threadIdx.x >> 5), quad = hw & 3, half = hw >= 6 ? 1 : 0, ml = quad * 32 + (cid & 31);
+                const uint32_t src = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)(half * 16 * p.ts_wbox + ml) * 4u;
+                float hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    hi[i] = 0.f;
+                    if (ml < p.ts_wbox) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[i]) : "r"(src + (uint32_t)(i * p.ts_wbox) * 4u));
+                    lo[i] = tf32_residual(hi[i]);
+                }
+                const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.ts_acol0 + ls * TS_COLS + half * 16);
+                tmem_st16(ta, hi);
+                tmem_st16(ta + BLOCK_K, lo);
+                // activations: residual slab in shared memory, as in the SS path but for the B part only
+                const uint32_t bhi = smem_u32(smem + (size_t)st * stage_bytes + A_STAGE_BYTES) + cid * 16;
+                const uint32_t blo = smem_u32(lo_base + (size_t)ls * lo_stage_bytes) + cid * 16;
+                for (uint32_t off = 0; off + cid * 16 < b_stage_bytes; off += NCONV * 16) {
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(bhi + off));
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
+                                 ::"r"(blo + off), "f"(tf32_residual(v.x)), "f"(tf32_residual(v.y)), "f"(tf32_residual(v.z)),
+                                   "f"(tf32_residual(v.w)) : "memory");
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core
+                tc_fence_before();                        // tensor-memory stores ordered before the arrive
+                mbar_arrive(&lo_ready[ls]);
+                if (kb < 40) DI_TRACE_T0(128 + kb);
+                continue;
+            }
             const uint32_t hi = smem_u32(smem + (size_t)st * stage_bytes) + cid * 16;
             const uint32_t lo = smem_u32(lo_base + (size_t)ls * stage_bytes) + cid * 16;
             for (int i0 = 0; i0 < per_thread; i0 += 4) {
@@ -252,7 +314,8 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
         if (elect_one()) {
             auto load_a = [&](int kb, int st) {
                 uint8_t* sa = smem + (size_t)st * stage_bytes;
-                if constexpr (A_MN) load_stage<true>(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K, TILE_M);
+                if constexpr (TS) tma_load_2d(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K);   // plain [32 k][wbox] tile
+                else if constexpr (A_MN) load_stage<true>(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K, TILE_M);
                 else tma_load_2d(sa, &mapA, &full_bar[st], a_c0 + kb * BLOCK_K, a_c1);
             };
             auto load_b = [&](int kb, int st) {
@@ -302,7 +365,17 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                 if (kb < 40) DI_TRACE(88 + kb);
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                 const uint32_t sb = sa + A_STAGE_BYTES;
-                if constexpr (X3) {
+                if constexpr (TS) {
+                    const uint32_t idesc_ts = idesc_for(p.n_cols, false, false);
+                    const uint32_t sb_lo = smem_u32(lo_base + (size_t)ls * lo_stage_bytes);
+                    const uint32_t ta = tmem + (uint32_t)(p.ts_acol0 + ls * TS_COLS);
+#pragma unroll
+                    for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
+                        umma_tf32_ts(tmem, ta + BLOCK_K + j * UMMA_K, stage_desc<false>(sb, j), idesc_ts, (kb | j) ? 1u : 0u);
+                        umma_tf32_ts(tmem, ta + j * UMMA_K, stage_desc<false>(sb_lo, j), idesc_ts, 1u);
+                        umma_tf32_ts(tmem, ta + j * UMMA_K, stage_desc<false>(sb, j), idesc_ts, 1u);
+                    }
+                } else if constexpr (X3) {
                     const uint32_t sa_lo = smem_u32(lo_base + (size_t)ls * stage_bytes), sb_lo = sa_lo + A_STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
@@ -941,6 +1014,9 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
 struct TcState {
     // weights / step buffers (fixed for the life of the engine)
     CUtensorMap W1_mn, W2_mn, W2_k;
+    CUtensorMap W1_ts, W2_ts;                              // plain [32 k][min(128, out)] weight tiles of the TS kernels
+    bool ts = true;                                        // FWD1 / FWD2 take the weights from tensor memory (DEEPIMPUTE_B200_TS=0: from shared memory)
+    int ts_stages = 0, ts_lo = 0, ts_smem1 = 0, ts_smem2 = 0, ts_tmem = 0, ts_acol0 = 0;
     CUtensorMap H_k, H_mn, DZ2_k, DZ2_mn, DZ1_mn;          // training activations [Bp][...]
     CUtensorMap Hlo_mn, DZ2lo_mn, DZ1lo_mn, Xstep_lo_mn, Xtr_lo_mn;   // residual twins (x3)
     CUtensorMap H_aux;                                     // h tile for the BWD epilogue
@@ -1067,6 +1143,8 @@ bool tc_init(Engine& e) {
     ok = ok && make_map_2d(&st->W1_mn, e.W1, e.PT, e.Hp, e.Hp, 32, true);
     ok = ok && make_map_2d(&st->W2_mn, e.W2, SH, e.Op, e.Op, 32, true);
     ok = ok && make_map_2d(&st->W2_k, e.W2, SH, e.Op, e.Op, TILE_M);
+    ok = ok && make_map_plain(&st->W1_ts, e.W1, e.PT, e.Hp, e.Hp, st->wbox1, BLOCK_K);
+    ok = ok && make_map_plain(&st->W2_ts, e.W2, SH, e.Op, e.Op, st->wbox2, BLOCK_K);
     ok = ok && make_map_2d(&st->H_k, e.Hact, e.Bp, SH, SH, e.Bp);
     ok = ok && make_map_2d(&st->H_mn, e.Hact, e.Bp, SH, SH, 32, true);
     ok = ok && make_map_plain(&st->H_aux, e.Hact, e.Bp, SH, SH, st->aux_h, e.Bp);
@@ -1117,6 +1195,25 @@ bool tc_init(Engine& e) {
         if (!st->fwd1_train[2].stages) { st->fwd1_train[2] = st->fwd1_train[0]; st->fwd2_train[2] = st->fwd2_train[0]; st->bwd_train[2] = st->bwd_train[0]; }
     }
     st->infer = pick_cfg(e.infer_tile, 0, st->x3, true);
+    // TS variant of the training FWD1 / FWD2 (X3 only): ring of [A | B] slabs + ring of B residual slabs + Y tile;
+    // tensor memory: accumulator (Bp columns) + one 64-column weight slab per residual stage
+    if (st->x3) {
+        if (const char* v = getenv("DEEPIMPUTE_B200_TS")) st->ts = atoi(v) != 0;
+        const int nb = e.Bp * BLOCK_K * 4;
+        st->ts_acol0 = (e.Bp + 31) / 32 * 32;
+        for (int hs = 6; hs >= 2 && st->ts; --hs) {
+            const int ls = std::min(hs, 4);
+            const int bytes1 = hs * ((int)A_STAGE_BYTES + nb) + ls * nb + 1024, bytes2 = bytes1 + aux_floats * 4;
+            if (bytes2 <= 224 * 1024 && st->ts_acol0 + ls * TS_COLS <= 512) {
+                st->ts_stages = hs; st->ts_lo = ls; st->ts_smem1 = bytes1; st->ts_smem2 = bytes2;
+                st->ts_tmem = pow2_cols(st->ts_acol0 + ls * TS_COLS);
+                break;
+            }
+        }
+        if (!st->ts_stages) st->ts = false;
+    } else {
+        st->ts = false;                // the TS kernels are instantiated for the compensated mode only
+    }
     // sub-network groups of the epoch graph: independent chains on their own streams
     int G = std::min(16, e.S);
     if (const char* v = getenv("DEEPIMPUTE_B200_GROUPS")) G = std::max(1, std::min(std::min((int)TcState::MAX_GROUPS, e.S), atoi(v)));
@@ -1169,6 +1266,10 @@ bool tc_init(Engine& e) {
     set((const void*)tc_kernel<TC_FWD2, false>, m2); set((const void*)tc_kernel<TC_FWD2, true>, m2);
     set((const void*)tc_kernel<TC_BWD, false>, m3);
     set((const void*)tc_kernel<TC_BWD, true>, m3);
+    if (st->ts) {
+        set((const void*)tc_kernel<TC_FWD1, true, true>, st->ts_smem1);
+        set((const void*)tc_kernel<TC_FWD2, true, true>, st->ts_smem2);
+    }
     set((const void*)tc_adam_kernel<false>, st->smem_adam);
     set((const void*)tc_adam_kernel<true>, st->smem_adam);
     if (st->adam_big) {
@@ -1225,13 +1326,13 @@ struct StepPlan {
     int deep = 0;                                // 1: deep-ring configs (one CTA per SM), for small grids
 };
 
-template <int OP, bool X3>
+template <int OP, bool X3, bool TS = false>
 void launch_on(Engine& e, const StepPlan& pl, const char* name, const CUtensorMap& a, const CUtensorMap& b,
                const CUtensorMap& c, const TcParams& p, dim3 grid, int smem) {
     const bool pdl = static_cast<TcState*>(e.tc)->pdl;
-    if (pl.graph) { launch_k(tc_kernel<OP, X3>, grid, X3 ? NTHREADS_X3 : NTHREADS, smem, pl.main, pdl, a, b, c, p); return; }
+    if (pl.graph) { launch_k(tc_kernel<OP, X3, TS>, grid, X3 ? NTHREADS_X3 : NTHREADS, smem, pl.main, pdl, a, b, c, p); return; }
     KernelTimer t(e, name);
-    launch_k(tc_kernel<OP, X3>, grid, X3 ? NTHREADS_X3 : NTHREADS, smem, pl.main, false, a, b, c, p);
+    launch_k(tc_kernel<OP, X3, TS>, grid, X3 ? NTHREADS_X3 : NTHREADS, smem, pl.main, false, a, b, c, p);
     count_launch(e, name);
 }
 
@@ -1259,12 +1360,19 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
 
     { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
       q.stages = c1.stages; q.lo_stages = c1.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace;
-      if (st->x3) launch_on<TC_FWD1, true>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem);
+      if (st->ts) {
+          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.ts_wbox = st->wbox1;
+          launch_on<TC_FWD1, true, true>(e, pl, "fwd1", st->W1_ts, Xk, Xk, q, dim3(1, mh, pl.ns), st->ts_smem1);
+      } else if (st->x3) launch_on<TC_FWD1, true>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem);
       else launch_on<TC_FWD1, false>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem); }
     { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
       q.stages = c2.stages; q.lo_stages = c2.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 256;
       if (c2.aux) { q.aux_cols = st->aux_y; q.aux_row0 = a.row0; }
-      if (st->x3) launch_on<TC_FWD2, true>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem);
+      if (st->ts) {
+          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.ts_wbox = st->wbox2;
+          q.aux_cols = st->aux_y; q.aux_row0 = a.row0;
+          launch_on<TC_FWD2, true, true>(e, pl, "fwd2", st->W2_ts, st->H_k, Yaux, q, dim3(1, mo, pl.ns), st->ts_smem2);
+      } else if (st->x3) launch_on<TC_FWD2, true>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem);
       else launch_on<TC_FWD2, false>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem); }
     { TcParams q = p; q.m_tiles = mh; q.row0 = 0;
       if (c3.aux) { q.aux_cols = st->aux_h; q.aux_row0 = 0; }
