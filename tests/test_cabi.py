@@ -59,6 +59,14 @@ def test_bad_arguments_are_rejected_before_touching_the_device():
     assert b"invalid" in lib.di_last_error(None)
     assert lib.di_predict(None, None, 0, None) == 1
     assert lib.di_launch_count(None) == 0
+    # the fused ends follow the same convention: a missing handle is an argument error
+    raw = np.zeros((2, 2), dtype=np.float32)
+    assert lib.di_upload_counts(None, C.c_void_p(raw.ctypes.data), 0, 2, 2) == 1
+    assert lib.di_impute(None, 1, None, 0, None, 0, 1, C.c_void_p(raw.ctypes.data)) == 1
+    # stand-alone predictor selection validates its arguments before it looks for a device
+    top = np.zeros(5, dtype=np.int32)
+    rc = lib.di_corr_topk(0, None, 0, 0, None, 0, None, 0, 0, 5, _lib.i32(top), None, None)
+    assert rc != 0 and lib.di_corr_last_error()
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
