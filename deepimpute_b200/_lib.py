@@ -45,6 +45,9 @@ SIGNATURES = {
     "di_predict": (C.c_int, [_H, _i32p, C.c_int64, _f32p]),
     "di_predict_device": (C.c_int, [_H, _i32p, C.c_int64, C.c_void_p, C.c_int64]),
     "di_impute": (C.c_int, [_H, C.c_int32, _i32p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "di_gene_stats": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_double),
+                                C.POINTER(C.c_double), _f32p]),
+    "di_gene_stats_last_error": (C.c_char_p, []),
     "di_corr_topk": (C.c_int, [C.c_int32, _f32p, C.c_int64, C.c_int64, _i32p, C.c_int64, _i32p, C.c_int32, C.c_int32,
                                C.c_int32, _i32p, _f32p, _f32p]),
     "di_corr_last_error": (C.c_char_p, []),

@@ -1,0 +1,121 @@
+// Per-gene mean and variance of the raw count matrix on the GPU.
+//
+// The reference derives both of its gene filters from pandas column reductions over the whole matrix: the imputation
+// ranking var / (1 + mean) (multinet.py:191-192) and the predictor-candidate filter std / mean > 0 (multinet.py:22-24).
+// pandas walks the N x G float64 frame three times on one core -- about 45 s at 50k cells x 20k genes, against
+// 1.4 s for the 20 training epochs that follow.  Here: one upload, two passes in HBM (mean, then the sum of squared
+// deviations around it -- the same two-pass form pandas' nanvar uses), everything accumulated in float64.
+// Summation order differs from pandas, so values agree to ~1e-15 relative; rankings can differ only between genes
+// whose statistics tie to that precision.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/deepimpute_b200.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+constexpr int ROWS_PER_BLOCK = 256;
+
+// acc[g] += sum over this block's rows of x (mean == nullptr) or of (x - mean[g])^2; one gene per thread, so a warp
+// reads 32 consecutive values of a row
+template <typename T>
+__global__ void __launch_bounds__(128) colstat_kernel(const T* __restrict__ x, int64_t N, int64_t G,
+                                                      const double* __restrict__ mean, double* __restrict__ acc) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const int64_t r0 = (int64_t)blockIdx.y * ROWS_PER_BLOCK, r1 = min(N, r0 + (int64_t)ROWS_PER_BLOCK);
+    const double m = mean ? mean[g] : 0.0;
+    double s0 = 0.0, s1 = 0.0;                            // two chains: the adds of consecutive rows overlap
+    int64_t r = r0;
+    if (mean) {
+        for (; r + 1 < r1; r += 2) {
+            const double a = (double)__ldcs(x + r * G + g) - m, b = (double)__ldcs(x + (r + 1) * G + g) - m;
+            s0 += a * a; s1 += b * b;
+        }
+        if (r < r1) { const double a = (double)__ldcs(x + r * G + g) - m; s0 += a * a; }
+    } else {
+        for (; r + 1 < r1; r += 2) { s0 += (double)__ldcs(x + r * G + g); s1 += (double)__ldcs(x + (r + 1) * G + g); }
+        if (r < r1) s0 += (double)__ldcs(x + r * G + g);
+    }
+    atomicAdd(acc + g, s0 + s1);
+}
+
+__global__ void finish_kernel(double* v, int64_t G, double denom) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g < G) v[g] /= denom;
+}
+
+template <typename T>
+void run_stats(const T* dx, int64_t N, int64_t G, double* dmean, double* dvar, cudaStream_t st) {
+    const dim3 grid((unsigned)((G + 127) / 128), (unsigned)((N + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK));
+    const unsigned fb = (unsigned)((G + 255) / 256);
+    colstat_kernel<T><<<grid, 128, 0, st>>>(dx, N, G, nullptr, dmean);
+    finish_kernel<<<fb, 256, 0, st>>>(dmean, G, (double)N);
+    colstat_kernel<T><<<grid, 128, 0, st>>>(dx, N, G, dmean, dvar);
+    finish_kernel<<<fb, 256, 0, st>>>(dvar, G, (double)(N - 1));          // ddof = 1 like pandas .var() / .std()
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* di_gene_stats_last_error(void) { return g_err.c_str(); }
+
+int di_gene_stats(int32_t device, const void* raw, int32_t dtype, int64_t n_cells, int64_t n_genes, double* mean_out,
+                  double* var_out, float* device_ms_out) {
+    if (!raw || !mean_out || !var_out || n_cells <= 1 || n_genes <= 0 || (dtype != DI_DTYPE_F32 && dtype != DI_DTYPE_F64)) {
+        g_err = "di_gene_stats: bad arguments";
+        return DI_ERR_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        g_err = "di_gene_stats: no such CUDA device (there is no CPU fallback)";
+        return DI_ERR_CUDA;
+    }
+    const size_t esz = dtype == DI_DTYPE_F64 ? sizeof(double) : sizeof(float);
+    const size_t bytes = (size_t)n_cells * n_genes * esz;
+    void* dx = nullptr;
+    double *dmean = nullptr, *dvar = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = DI_OK;
+    auto check = [&](cudaError_t err, const char* what) {
+        if (err != cudaSuccess && rc == DI_OK) {
+            g_err = std::string("di_gene_stats: ") + what + " failed: " + cudaGetErrorString(err);
+            rc = err == cudaErrorMemoryAllocation ? DI_ERR_OOM : DI_ERR_CUDA;
+        }
+        return err == cudaSuccess;
+    };
+    if (check(cudaSetDevice(device), "cudaSetDevice") &&
+        check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate") &&
+        check(cudaEventCreate(&e0), "cudaEventCreate") && check(cudaEventCreate(&e1), "cudaEventCreate") &&
+        check(cudaMalloc(&dx, bytes), "cudaMalloc(matrix)") &&
+        check(cudaMalloc((void**)&dmean, (size_t)n_genes * sizeof(double)), "cudaMalloc") &&
+        check(cudaMalloc((void**)&dvar, (size_t)n_genes * sizeof(double)), "cudaMalloc") &&
+        check(cudaMemcpyAsync(dx, raw, bytes, cudaMemcpyHostToDevice, st), "upload") &&
+        check(cudaMemsetAsync(dmean, 0, (size_t)n_genes * sizeof(double), st), "memset") &&
+        check(cudaMemsetAsync(dvar, 0, (size_t)n_genes * sizeof(double), st), "memset") &&
+        check(cudaEventRecord(e0, st), "cudaEventRecord")) {
+        if (dtype == DI_DTYPE_F64) run_stats(static_cast<const double*>(dx), n_cells, n_genes, dmean, dvar, st);
+        else run_stats(static_cast<const float*>(dx), n_cells, n_genes, dmean, dvar, st);
+        check(cudaGetLastError(), "kernel launch");
+        check(cudaEventRecord(e1, st), "cudaEventRecord");
+        check(cudaMemcpyAsync(mean_out, dmean, (size_t)n_genes * sizeof(double), cudaMemcpyDeviceToHost, st), "download");
+        check(cudaMemcpyAsync(var_out, dvar, (size_t)n_genes * sizeof(double), cudaMemcpyDeviceToHost, st), "download");
+        check(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+        if (rc == DI_OK && device_ms_out) check(cudaEventElapsedTime(device_ms_out, e0, e1), "cudaEventElapsedTime");
+    }
+    if (dx) cudaFree(dx);
+    if (dmean) cudaFree(dmean);
+    if (dvar) cudaFree(dvar);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+}  // extern "C"

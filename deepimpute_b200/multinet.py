@@ -66,7 +66,8 @@ class MultiNet:
     """Drop-in for ``deepimpute.multinet.MultiNet`` (reference ``multinet.py:65-375``).
 
     Extra keyword-only arguments (not in the reference): ``math_mode`` ("tf32x3" tensor-core kernels, default; "tf32"; or
-    "fp32" CUDA-core kernels), ``postprocess`` ("gpu": fused device-side ``log1p`` / imputation tail, default; "host": numpy),
+    "fp32" CUDA-core kernels), ``postprocess`` ("gpu": fused device-side ``log1p`` / imputation tail, default; "host": numpy), ``stats_engine`` /
+    ``predictor_engine`` ("auto": per-gene statistics / correlations on the GPU for large inputs, pandas / numpy otherwise),
     ``device`` (CUDA ordinal) and ``shard`` (a ``parallel.ShardContext``: this process
     trains only its share of the sub-networks and the per-epoch losses / predicted blocks are exchanged with the
     other ranks; see ``deepimpute_b200.parallel``).
@@ -90,6 +91,7 @@ class MultiNet:
                  shard=None,
                  predictor_engine="auto",
                  postprocess="gpu",
+                 stats_engine="auto",
                  ):
         self.NN_parameters = {"learning_rate": learning_rate,
                               "batch_size": batch_size,
@@ -109,6 +111,11 @@ class MultiNet:
         if predictor_engine not in ("auto", "host", "gpu"):
             raise ValueError("predictor_engine must be 'auto', 'host' or 'gpu'")
         self.predictor_engine = predictor_engine
+        if stats_engine not in ("auto", "host", "gpu"):
+            raise ValueError("stats_engine must be 'auto', 'host' or 'gpu'")
+        # per-gene mean / variance behind both gene filters (multinet.py:191-192, :22-24): pandas reductions on the host
+        # (bit-for-bit the reference's numbers) or di_gene_stats on the GPU (large inputs: pandas needs ~45 s at 50k x 20k)
+        self.stats_engine = stats_engine
         if postprocess not in ("gpu", "host"):
             raise ValueError("postprocess must be 'gpu' or 'host'")
         # "gpu": log1p of the counts and the whole tail of predict (multinet.py:217, :271, :282-303) run on the device
@@ -251,7 +258,16 @@ class MultiNet:
             raw = raw.sample(frac=cell_subset) if cell_subset < 1 else raw.sample(int(cell_subset))
 
         cols = raw.columns
-        self._ranked, self._metric = partition.rank_genes(raw)
+        raw_values = raw.values
+        import time as _time
+        t0 = _time.perf_counter()
+        gpu_stats = self.stats_engine == "gpu" or (self.stats_engine == "auto" and raw_values.size >= 2e8)
+        if gpu_stats:
+            mean, var, ms = partition.gene_stats_gpu(raw_values, device=self.device if self.device is not None else 0)
+            self.timings["gene_stats_device_ms"] = ms
+            self._ranked, self._metric = partition.rank_genes_from_stats(mean, var)
+        else:
+            self._ranked, self._metric = partition.rank_genes(raw)
         if genes_to_impute is None:
             genes = partition.choose_genes(self._ranked, self._metric, self.sub_outputdim, minVMR, NN_lim)
             print("{} genes selected for imputation".format(len(genes)))
@@ -262,14 +278,17 @@ class MultiNet:
                       .format(len(user)))
             genes = partition.pad_user_genes(user, self._ranked, self.sub_outputdim)
 
-        raw_values = raw.values
-        cand = partition.candidate_predictors(raw, n_pred)
+        if gpu_stats:
+            cand = partition.candidate_predictors_from_stats(mean, var, n_pred)
+        else:
+            cand = partition.candidate_predictors(raw, n_pred)
+        self.timings["gene_stats_s"] = _time.perf_counter() - t0
+        self.timings["stats_engine"] = "gpu" if gpu_stats else "host"
         # the correlation matrix is O(G^2 N): float64 numpy on the host for small inputs (bit-for-bit the reference's
         # selection), the GPU (fp32, di_corr_topk) for large ones, where the host takes minutes
         use_gpu = self.predictor_engine == "gpu" or (
             self.predictor_engine == "auto" and n_pred is None and
             float(len(cand)) ** 2 * raw.shape[0] >= 2e11)
-        import time as _time
         t0 = _time.perf_counter()
         if use_gpu:
             self._set_partition_gpu(cols, raw_values, genes, cand, ntop, mode)

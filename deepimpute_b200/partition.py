@@ -34,6 +34,45 @@ def rank_genes(raw):
     return metric.index.values.astype(np.int64), metric.values
 
 
+def gene_stats_gpu(raw_values, device=0):
+    """Per-gene (mean, variance with ddof = 1) of the count matrix on the GPU (``di_gene_stats``), float64.
+    Returns (mean, var, device milliseconds)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    x = np.asarray(raw_values)
+    if x.dtype != np.float32:
+        x = x.astype(np.float64, copy=False)
+    x = np.ascontiguousarray(x)
+    mean, var = np.empty(x.shape[1], np.float64), np.empty(x.shape[1], np.float64)
+    ms = C.c_float()
+    dp = C.POINTER(C.c_double)
+    rc = lib.di_gene_stats(int(device), C.c_void_p(x.ctypes.data), _lib.DI_DTYPE[x.dtype.name], x.shape[0], x.shape[1],
+                           mean.ctypes.data_as(dp), var.ctypes.data_as(dp), C.byref(ms))
+    if rc != 0:
+        raise RuntimeError("di_gene_stats failed ({}): {}".format(rc, lib.di_gene_stats_last_error().decode()))
+    return mean, var, ms.value
+
+
+def rank_genes_from_stats(mean, var):
+    """``rank_genes`` from precomputed per-gene statistics (same ranking rule, ``multinet.py:191-192``)."""
+    metric = pd.Series(var / (1 + mean), index=np.arange(len(mean))).sort_values(ascending=False)
+    metric = metric[metric > 0]
+    return metric.index.values.astype(np.int64), metric.values
+
+
+def candidate_predictors_from_stats(mean, var, n_pred=None):
+    """``candidate_predictors`` from precomputed per-gene statistics (``multinet.py:22-29``)."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        cv = np.sqrt(var) / mean
+    cv[np.isinf(cv)] = 0
+    cv = pd.Series(cv, index=np.arange(len(mean)))
+    if n_pred is None:
+        return np.flatnonzero((cv > 0).values)
+    print("Using {} predictors".format(n_pred))
+    return cv.sort_values(ascending=False).index.values[:n_pred].astype(np.int64)
+
+
 def choose_genes(ranked, metric_values, sub_outputdim, threshold, limit=None):
     """Genes to impute, padded with random filler genes to a multiple of ``sub_outputdim``.
 

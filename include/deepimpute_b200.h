@@ -132,6 +132,15 @@ int di_predict_device(di_handle* h, const int32_t* rows, int64_t n, float* d_out
 int di_impute(di_handle* h, int32_t policy, const int32_t* slot_gene, int64_t n_slots, const float* d_pred,
               int64_t ld_pred, int32_t out_dtype, void* out);
 
+/* Per-gene mean and variance (ddof = 1, like pandas .var()) of raw[n_cells][n_genes] (dtype DI_DTYPE_F32 / _F64), in
+ * float64: the inputs of both gene filters of fit -- the imputation ranking var / (1 + mean), multinet.py:191-192, and
+ * the predictor-candidate filter std / mean > 0, multinet.py:22-24 -- which pandas computes in three single-core passes
+ * over the frame.  Stand-alone like di_corr_topk (no handle; allocates and frees its own device memory).  Two passes
+ * (mean, then squared deviations): values agree with pandas to ~1e-15 relative. */
+int di_gene_stats(int32_t device, const void* raw, int32_t dtype, int64_t n_cells, int64_t n_genes, double* mean_out,
+                  double* var_out, float* device_ms_out);
+const char* di_gene_stats_last_error(void);
+
 /* Predictor selection (the O(G^2 N) step of fit).  |Pearson r| between genes on RAW
  * counts raw[n_cells][n_genes] -- get_distance_matrix, multinet.py:20-34: abs(np.corrcoef(raw.T)), NaN -> 0 -- and for
  * every target gene targ[s][o] the ntop (<= 8) most correlated candidates that are not targets of sub-network s --

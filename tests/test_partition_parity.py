@@ -155,3 +155,24 @@ def test_live_reference_named_methods(test_counts):
     # (Arrow-backed column labels have no reshape), so the expectation is written out
     mine.setTargets(raw.reindex(columns=g_mine), mode="progressive")
     np.testing.assert_array_equal(mine.targets, np.asarray(list(g_mine), dtype=object).reshape(-1, 128))
+
+
+def test_statistics_based_filters_equal_the_pandas_ones(test_counts):
+    """``rank_genes_from_stats`` / ``candidate_predictors_from_stats`` (fed by ``di_gene_stats`` on large inputs) apply
+    the same rules as the pandas forms: with pandas' own mean / var they reproduce ranking and candidates exactly."""
+    from deepimpute_b200 import partition
+    raw = test_counts
+    mean, var = raw.mean().values, raw.var().values
+    ranked, metric = partition.rank_genes(raw)
+    ranked2, metric2 = partition.rank_genes_from_stats(mean, var)
+    np.testing.assert_array_equal(ranked, ranked2)
+    np.testing.assert_array_equal(metric, metric2)
+    for n_pred in (None, 700):
+        np.testing.assert_array_equal(partition.candidate_predictors(raw, n_pred),
+                                      partition.candidate_predictors_from_stats(mean, var, n_pred))
+    # a gene that is zero everywhere has mean 0 and variance 0: std / mean = NaN -> not a candidate, metric 0 -> not ranked
+    raw0 = raw.copy()
+    raw0.iloc[:, 5] = 0.0
+    m0, v0 = raw0.mean().values, raw0.var().values
+    assert 5 not in partition.candidate_predictors_from_stats(m0, v0) and 5 not in partition.rank_genes_from_stats(m0, v0)[0]
+    np.testing.assert_array_equal(partition.candidate_predictors(raw0), partition.candidate_predictors_from_stats(m0, v0))
