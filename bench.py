@@ -111,7 +111,8 @@ def build_workload(name, device):
     np.random.seed(MODEL_SEED)
     train_rows, test_rows = partition.split_cells(N)
     raw_host = None
-    if os.environ.get("DI_BENCH_PREDICTORS", "1") != "0" and dev.type == "cuda":
+    # the raw counts are only needed by the single-GPU side blocks (predictor selection, fused post-processing)
+    if os.environ.get("DI_BENCH_PREDICTORS", "1") != "0" and dev.type == "cuda" and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         raw_host = torch.empty((N, G), dtype=torch.float32, pin_memory=True)
         raw_host.copy_(raw_keep)
     del raw_keep, raw
