@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t b_stage_bytes = (uint32_t)p.n_cols * BLOCK_K * 4;
     // one slab: [A | B], what TMA writes per K block (TS: the A part is a plain [32][ts_wbox] tile)
-    const uint32_t hi_bytes = (TS ? (uint32_t)(BLOCK_K * p.ts_wbox * 4) : A_STAGE_BYTES) + b_stage_bytes;
+    const uint32_t hi_bytes = ((TS && A_MN) ? (uint32_t)(BLOCK_K * p.ts_wbox * 4) : A_STAGE_BYTES) + b_stage_bytes;
     const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
     const uint32_t lo_stage_bytes = TS ? b_stage_bytes : stage_bytes;  // TS: only the activation slab has a residual in smem
     const int stages = p.stages;
@@ -259,14 +259,29 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                 // weights: this thread owns feature `quad * 32 + lane` (the TMEM lane its warp may write) and half of the
                 // slab's 32 k; W and its residual go to tensor memory, columns [ls * 64, +32) and [ls * 64 + 32, +32)
                 const int hw = (int)(threadIdx.x >> 5), quad = hw & 3, half = hw >= 6 ? 1 : 0, ml = quad * 32 + (cid & 31);
-                const uint32_t src = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)(half * 16 * p.ts_wbox + ml) * 4u;
                 float hi[16], lo[16];
+                if constexpr (A_MN) {
+                    // FWD1 / FWD2: plain [32 k][wbox features] tile; a warp reads 32 consecutive features of one k
+                    const uint32_t src = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)(half * 16 * p.ts_wbox + ml) * 4u;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    hi[i] = 0.f;
-                    if (ml < p.ts_wbox) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[i]) : "r"(src + (uint32_t)(i * p.ts_wbox) * 4u));
-                    lo[i] = tf32_residual(hi[i]);
+                    for (int i = 0; i < 16; ++i) {
+                        hi[i] = 0.f;
+                        if (ml < p.ts_wbox) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[i]) : "r"(src + (uint32_t)(i * p.ts_wbox) * 4u));
+                    }
+                } else {
+                    // BWD: K-major tile written by TMA with the 128-byte swizzle: row = feature (128 B = 32 k), the 16-byte
+                    // chunk c of row m sits at chunk c ^ (m & 7); this thread's 16 k are chunks 4 half .. 4 half + 3
+                    // (eight consecutive rows hit eight different chunks: conflict-free 16-byte loads)
+                    const uint32_t rowb = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)ml * 128u;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t chunk = (uint32_t)((half * 4 + c) ^ (ml & 7));
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(hi[4 * c]), "=f"(hi[4 * c + 1]), "=f"(hi[4 * c + 2]), "=f"(hi[4 * c + 3]) : "r"(rowb + chunk * 16u));
+                    }
                 }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) lo[i] = tf32_residual(hi[i]);
                 const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.ts_acol0 + ls * TS_COLS + half * 16);
                 tmem_st16(ta, hi);
                 tmem_st16(ta + BLOCK_K, lo);
@@ -314,7 +329,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
         if (elect_one()) {
             auto load_a = [&](int kb, int st) {
                 uint8_t* sa = smem + (size_t)st * stage_bytes;
-                if constexpr (TS) tma_load_2d(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K);   // plain [32 k][wbox] tile
+                if constexpr (TS && A_MN) tma_load_2d(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K);   // plain [32 k][wbox] tile
                 else if constexpr (A_MN) load_stage<true>(sa, &mapA, &full_bar[st], a_c0, a_c1 + kb * BLOCK_K, TILE_M);
                 else tma_load_2d(sa, &mapA, &full_bar[st], a_c0 + kb * BLOCK_K, a_c1);
             };
@@ -1016,6 +1031,7 @@ struct TcState {
     CUtensorMap W1_mn, W2_mn, W2_k;
     CUtensorMap W1_ts, W2_ts;                              // plain [32 k][min(128, out)] weight tiles of the TS kernels
     bool ts = true;                                        // FWD1 / FWD2 take the weights from tensor memory (DEEPIMPUTE_B200_TS=0: from shared memory)
+    bool ts_bwd = false;                                   // DEEPIMPUTE_B200_TS_BWD=1: BWD too (written, not yet run on hardware)
     int ts_stages = 0, ts_lo = 0, ts_smem1 = 0, ts_smem2 = 0, ts_tmem = 0, ts_acol0 = 0;
     CUtensorMap H_k, H_mn, DZ2_k, DZ2_mn, DZ1_mn;          // training activations [Bp][...]
     CUtensorMap Hlo_mn, DZ2lo_mn, DZ1lo_mn, Xstep_lo_mn, Xtr_lo_mn;   // residual twins (x3)
@@ -1211,6 +1227,7 @@ bool tc_init(Engine& e) {
             }
         }
         if (!st->ts_stages) st->ts = false;
+        if (const char* v = getenv("DEEPIMPUTE_B200_TS_BWD")) st->ts_bwd = st->ts && atoi(v) != 0;
     } else {
         st->ts = false;                // the TS kernels are instantiated for the compensated mode only
     }
@@ -1269,6 +1286,7 @@ bool tc_init(Engine& e) {
     if (st->ts) {
         set((const void*)tc_kernel<TC_FWD1, true, true>, st->ts_smem1);
         set((const void*)tc_kernel<TC_FWD2, true, true>, st->ts_smem2);
+        if (st->ts_bwd) set((const void*)tc_kernel<TC_BWD, true, true>, st->ts_smem2);
     }
     set((const void*)tc_adam_kernel<false>, st->smem_adam);
     set((const void*)tc_adam_kernel<true>, st->smem_adam);
@@ -1377,7 +1395,11 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     { TcParams q = p; q.m_tiles = mh; q.row0 = 0;
       if (c3.aux) { q.aux_cols = st->aux_h; q.aux_row0 = 0; }
       q.stages = c3.stages; q.lo_stages = c3.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 512;
-      if (st->x3) launch_on<TC_BWD, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem);
+      if (st->ts_bwd) {
+          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.ts_wbox = TILE_M;
+          q.aux_cols = st->aux_h; q.aux_row0 = 0;
+          launch_on<TC_BWD, true, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), st->ts_smem2);
+      } else if (st->x3) launch_on<TC_BWD, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem);
       else launch_on<TC_BWD, false>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem); }
     if (st->simt_adam && !pl.graph) { simt_adam_only(e, a); return; }
     TcParams q = p;
