@@ -417,6 +417,13 @@ def main():
     kern = {k: (eng.kernel_ms(k), eng.kernel_launches(k)) for k in names if eng.kernel_launches(k) > 0}
     eng.set_profiling(False)
     epoch_ms = eng.last_device_ms()
+    # the inference pass on its own (the tensor-pipe bound part of the path): device time of one predict
+    predict_ms = None
+    try:
+        eng.predict_device(out_dev.data_ptr(), pad_width)
+        predict_ms = float(eng.last_device_ms())
+    except Exception as exc:                                            # never lose the bench line over a side figure
+        print("bench.py: predict timing skipped ({})".format(exc), file=sys.stderr)
 
     # max over ranks
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -449,6 +456,12 @@ def main():
                     "unit": "GB/s", "frac": round(achieved / peaks["hbm"], 4),
                     "traffic": load_traffic(wl["name"], top, n_pred), "peak_source": peaks["source"],
                     "algorithmic_bytes_per_launch": work[top]["bytes"],
+                    "predict": None if not predict_ms else {
+                        "ms": round(predict_ms, 3), "bound": "tensor",
+                        "TFLOP/s_fp32_equivalent": round(sum(2.0 * N * (p * HIDDEN + HIDDEN * OUT) for p in n_pred)
+                                                         / (predict_ms * 1e-3) / 1e12, 2),
+                        "note": "gathers + FWD1 + FWD2 over all cells of this rank's sub-networks; tf32x3 issues three "
+                                "TF32 products per fp32-equivalent product"},
                     "train_step": {"ms": round(step_ms, 4), "GB/s": round(step_bytes / (step_ms * 1e-3) / 1e9, 1),
                                    "frac": round(step_bytes / (step_ms * 1e-3) / 1e9 / peaks["hbm"], 4),
                                    "TFLOP/s": round(step_flops / (step_ms * 1e-3) / 1e12, 2),
