@@ -410,7 +410,9 @@ class MultiNet:
             else:   # sharded: all-gather the prediction blocks on the devices, every rank finishes its own copy
                 full = self.shard.gather_blocks_device(model.predict_block(), self._owned, self.sub_outputdim)
                 values = model.impute(policy=policy, pred=full, slot_gene=targ_pos)
-            imputed = pd.DataFrame(values, index=raw.index, columns=raw.columns)
+            # the matrix is freshly allocated and owned by this call: wrap it, do not copy it (pandas would otherwise
+            # duplicate all N x G float64 values: ~2 s per GB)
+            imputed = pd.DataFrame(values, index=raw.index, columns=raw.columns, copy=False)
             if imputed_only:
                 return imputed.loc[:, np.unique(targets_flat)]
             return imputed
@@ -446,7 +448,7 @@ class MultiNet:
             mask = (raw.values > imputed)
             imputed[mask] = raw.values[mask]
 
-        imputed = pd.DataFrame(imputed, index=raw.index, columns=raw.columns)
+        imputed = pd.DataFrame(imputed, index=raw.index, columns=raw.columns, copy=False)
 
         if imputed_only:
             return imputed.loc[:, uniq_labels]
