@@ -258,7 +258,9 @@ class MultiNet:
             raw = raw.sample(frac=cell_subset) if cell_subset < 1 else raw.sample(int(cell_subset))
 
         cols = raw.columns
-        raw_values = raw.values
+        # pandas keeps a homogeneous frame gene-major, so ``raw.values`` is a transposed view: make the cell-major copy the
+        # engine wants ONCE and hand the same array to every consumer (statistics, correlations, upload)
+        raw_values = np.ascontiguousarray(raw.values)
         import time as _time
         t0 = _time.perf_counter()
         gpu_stats = self.stats_engine == "gpu" or (self.stats_engine == "auto" and raw_values.size >= 2e8)
