@@ -485,6 +485,7 @@ def main():
                     "h2d_bytes_per_step": int(N * G * 4 + args.epochs * n_train * 4),
                     "d2h_bytes_per_step": int(N * (width if world == 1 else pad_width * world) * 4)},
             "gpu_launches": launches,
+            "engine": eng.describe(), "graph_fallbacks": eng.graph_fallbacks(),
             "roofline": roofline,
         }
         if world == 1 and wl.get("raw") is not None:

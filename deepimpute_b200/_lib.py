@@ -60,6 +60,8 @@ SIGNATURES = {
     "di_kernel_ms": (C.c_float, [_H, C.c_char_p]),
     "di_kernel_launches": (C.c_int64, [_H, C.c_char_p]),
     "di_debug_read": (C.c_int, [_H, C.c_char_p, _f32p, C.c_int64, _i64p]),
+    "di_describe": (C.c_char_p, [_H]),
+    "di_graph_fallbacks": (C.c_int64, [_H]),
     "di_version": (C.c_int, []),
     "di_math_mode_available": (C.c_int, [C.c_int32]),
 }

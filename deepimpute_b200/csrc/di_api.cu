@@ -126,7 +126,7 @@ int sync_check(Engine& e) {
 
 void free_split(Engine& e) {
     dev_free(e.d_train_rows); dev_free(e.d_test_rows); dev_free(e.d_perm);
-    dev_free(e.Xtr); dev_free(e.Ytr); dev_free(e.Xte); dev_free(e.Yte); dev_free(e.Xtr_lo);
+    dev_free(e.Xtr); dev_free(e.Ytr); dev_free(e.Xte); dev_free(e.Yte); dev_free(e.Xtr_lo); dev_free(e.Xte_lo);
     e.n_train = e.n_test = e.n_train_pad = e.n_test_pad = 0;
 }
 
@@ -228,13 +228,18 @@ int di_create(di_handle** out, const di_config* cfg, const int32_t* n_pred) {
         if ((rc = dev_alloc(e, &e.d_desc, e.S))) return rc;
         DI_CUDA(cudaMemcpyAsync(e.d_desc, desc.data(), sizeof(SubnetDesc) * e.S, cudaMemcpyHostToDevice, e.stream));
         const int64_t n1 = e.PT * e.Hp, nb1 = (int64_t)e.S * e.Hp, n2 = (int64_t)e.S * e.Hp * e.Op, nb2 = (int64_t)e.S * e.Op;
-        float** w1[] = {&e.W1, &e.mW1, &e.vW1}; float** bb1[] = {&e.b1, &e.mb1, &e.vb1};
-        float** w2[] = {&e.W2, &e.mW2, &e.vW2}; float** bb2[] = {&e.b2, &e.mb2, &e.vb2};
-        for (int i = 0; i < 3; ++i) {
-            if ((rc = dev_alloc(e, w1[i], n1))) return rc;
-            if ((rc = dev_alloc(e, bb1[i], nb1))) return rc;
-            if ((rc = dev_alloc(e, w2[i], n2))) return rc;
-            if ((rc = dev_alloc(e, bb2[i], nb2))) return rc;
+        {   // one slab: [W1 mW1 vW1 W2 mW2 vW2 | W1lo W2lo | biases and their moments]; every block a multiple of 128 B
+            const bool x3 = cfg->math_mode == DI_MATH_TF32X3;
+            const int64_t total = 3 * n1 + 3 * n2 + (x3 ? n1 + n2 : 0) + 3 * nb1 + 3 * nb2;
+            if ((rc = dev_alloc(e, &e.state_slab, total))) return rc;
+            e.state_bytes = (size_t)total * sizeof(float);
+            float* q = e.state_slab;
+            auto take = [&](float** dst, int64_t n) { *dst = q; q += n; };
+            take(&e.W1, n1); take(&e.mW1, n1); take(&e.vW1, n1);
+            take(&e.W2, n2); take(&e.mW2, n2); take(&e.vW2, n2);
+            if (x3) { take(&e.W1lo, n1); take(&e.W2lo, n2); }
+            take(&e.b1, nb1); take(&e.mb1, nb1); take(&e.vb1, nb1);
+            take(&e.b2, nb2); take(&e.mb2, nb2); take(&e.vb2, nb2);
         }
         if ((rc = dev_alloc(e, &e.d_pred_cols, e.PT))) return rc;
         if ((rc = dev_alloc(e, &e.d_targ_cols, nb2))) return rc;
@@ -264,6 +269,10 @@ int di_create(di_handle** out, const di_config* cfg, const int32_t* n_pred) {
         if ((rc = dev_alloc(e, &e.Hchunk, cr * nb1))) return rc;
         if ((rc = dev_alloc(e, &e.Ochunk, cr * nb2))) return rc;
         if ((rc = dev_alloc(e, &e.OchunkB, cr * nb2))) return rc;
+        if (cfg->math_mode == DI_MATH_TF32X3) {
+            if ((rc = dev_alloc(e, &e.Xchunk_lo, cr * e.PT))) return rc;
+            if ((rc = dev_alloc(e, &e.Hchunk_lo, cr * nb1))) return rc;
+        }
         e.Ochunk2[0] = e.Ochunk; e.Ochunk2[1] = e.OchunkB;
         if ((rc = dev_alloc(e, &e.d_chunk_rows, cr))) return rc;
         for (int i = 0; i < 2; ++i) {
@@ -288,9 +297,8 @@ void di_destroy(di_handle* h) {
     tc_destroy(e);
     free_split(e);
     dev_free(e.d_desc); dev_free(e.d_norm); dev_free(e.d_pred_cols); dev_free(e.d_targ_cols);
-    float** all[] = {&e.W1, &e.mW1, &e.vW1, &e.b1, &e.mb1, &e.vb1, &e.W2, &e.mW2, &e.vW2, &e.b2, &e.mb2, &e.vb2,
-                     &e.Xstep, &e.Ystep, &e.Hact, &e.DZ2, &e.DZ1, &e.Xchunk, &e.Hchunk, &e.Ochunk, &e.OchunkB,
-                     &e.Hlo, &e.DZ2lo, &e.DZ1lo, &e.Xstep_lo};
+    float** all[] = {&e.state_slab, &e.Xstep, &e.Ystep, &e.Hact, &e.DZ2, &e.DZ1, &e.Xchunk, &e.Hchunk, &e.Ochunk, &e.OchunkB,
+                     &e.Hlo, &e.DZ2lo, &e.DZ1lo, &e.Xstep_lo, &e.Xchunk_lo, &e.Hchunk_lo};
     for (float** p : all) dev_free(*p);
     dev_free(e.d_step_rows); dev_free(e.d_chunk_rows); dev_free(e.d_loss);
     dev_free(e.d_raw_max); dev_free(e.d_gene_off); dev_free(e.d_gene_slots);
@@ -447,13 +455,14 @@ int di_set_split(di_handle* h, const int32_t* train_rows, int64_t n_train, const
         if (e.cfg.math_mode == DI_MATH_TF32X3 && (rc = dev_alloc(e, &e.Xtr_lo, e.n_train_pad * e.PT, false))) return rc;
         if ((rc = dev_alloc(e, &e.Ytr, e.n_train_pad * ldy, false))) return rc;
         if ((rc = dev_alloc(e, &e.Xte, e.n_test_pad * e.PT, false))) return rc;
+        if (e.cfg.math_mode == DI_MATH_TF32X3 && (rc = dev_alloc(e, &e.Xte_lo, e.n_test_pad * e.PT, false))) return rc;
         if ((rc = dev_alloc(e, &e.Yte, e.n_test_pad * ldy, false))) return rc;
     }
     e.split_stale = false;
     if (n_train) DI_CUDA(cudaMemcpyAsync(e.d_train_rows, train_rows, n_train * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
     if (n_test) DI_CUDA(cudaMemcpyAsync(e.d_test_rows, test_rows, n_test * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
     // held-out matrices are staged once; training matrices are re-gathered in shuffled order every epoch
-    launch_gather_xy(e, e.d_test_rows, nullptr, e.n_test_pad, n_test, 0, 0, e.Xte, nullptr, e.Yte);
+    launch_gather_xy(e, e.d_test_rows, nullptr, e.n_test_pad, n_test, 0, 0, e.Xte, e.Xte_lo, e.Yte);
     if (!reuse && e.cfg.math_mode != DI_MATH_FP32 && !tc_rebind(e)) return DI_ERR_CUDA;
     return sync_check(e);
 }
@@ -497,8 +506,11 @@ int di_set_weights(di_handle* h, int32_t s, const float* W1, const float* b1, co
         DI_CUDA(cudaMemsetAsync(bb2[i] + (int64_t)s * e.Op, 0, (size_t)e.Op * sizeof(float), e.stream));
     }
     e.adam_t = 0;
-    return weights_xfer(h, s, const_cast<float*>(W1), const_cast<float*>(b1), const_cast<float*>(W2),
-                        const_cast<float*>(b2), 0, true);
+    int rc = weights_xfer(h, s, const_cast<float*>(W1), const_cast<float*>(b1), const_cast<float*>(W2),
+                          const_cast<float*>(b2), 0, true);
+    if (rc) return rc;
+    if (e.cfg.math_mode != DI_MATH_FP32) { tc_weights_changed(e, s); rc = sync_check(e); }
+    return rc;
 }
 
 int di_get_weights(di_handle* h, int32_t s, float* W1, float* b1, float* W2, float* b2) {
@@ -613,7 +625,7 @@ static int predict_impl(di_handle* h, const int32_t* rows, int64_t n, float* hos
         const int64_t valid = std::min(e.chunk_rows, n - r0);
         const int64_t rows_pad = round_up64(valid, e.infer_tile);
         if (rows) DI_CUDA(cudaMemcpyAsync(e.d_chunk_rows, rows + r0, valid * sizeof(int32_t), cudaMemcpyHostToDevice, e.stream));
-        launch_gather(e, rows ? e.d_chunk_rows : nullptr, nullptr, r0, rows_pad, valid, e.d_pred_cols, e.PT, e.Xchunk);
+        launch_gather(e, rows ? e.d_chunk_rows : nullptr, nullptr, r0, rows_pad, valid, e.d_pred_cols, e.PT, e.Xchunk, 0, 0, e.Xchunk_lo);
         if (d_out) {
             run_forward(e, 3, e.Xchunk, nullptr, 0, rows_pad, valid, d_out + r0 * ld_out, ld_out);
         } else if (direct) {
@@ -733,7 +745,7 @@ int di_impute(di_handle* h, int32_t policy, const int32_t* slot_gene, int64_t n_
             pred = d_pred + r0 * ld_pred;
         } else {
             const int64_t rows_pad = round_up64(valid, e.infer_tile);
-            launch_gather(e, nullptr, nullptr, r0, rows_pad, valid, e.d_pred_cols, e.PT, e.Xchunk);
+            launch_gather(e, nullptr, nullptr, r0, rows_pad, valid, e.d_pred_cols, e.PT, e.Xchunk, 0, 0, e.Xchunk_lo);
             run_forward(e, 3, e.Xchunk, nullptr, 0, rows_pad, valid, e.Ochunk2[buf], SO);
             pred = e.Ochunk2[buf];
         }
@@ -801,6 +813,13 @@ int64_t di_kernel_launches(const di_handle* h, const char* which) {
     auto it = h->e.kernel_ms.find(which);
     return it == h->e.kernel_ms.end() ? 0 : it->second.second;
 }
+
+const char* di_describe(di_handle* h) {
+    if (!h) return "";
+    return h->e.cfg.math_mode == DI_MATH_FP32 ? "fp32 CUDA-core kernels" : tc_describe(h->e);
+}
+
+int64_t di_graph_fallbacks(di_handle* h) { return (h && h->e.cfg.math_mode != DI_MATH_FP32) ? tc_fallbacks(h->e) : 0; }
 
 int di_debug_read(di_handle* h, const char* which, float* out, int64_t capacity_floats, int64_t* ld) {
     if (!h || !which || !out || !ld) return DI_ERR_ARG;

@@ -57,10 +57,15 @@ struct Engine {
     int64_t imp_rows = 0; size_t imp_bytes = 0;
     bool split_stale = false;       // partition changed since di_set_split: staged matrices must be refilled
 
+    // weights, Adam moments and (DI_MATH_TF32X3) the residual twins of the weights live in ONE allocation, so that a
+    // single L2 access-policy window can cover the whole optimiser state (kernels_tc.cu: l2_window)
+    float* state_slab = nullptr;
+    size_t state_bytes = 0;
     float *W1 = nullptr, *mW1 = nullptr, *vW1 = nullptr;
     float *b1 = nullptr, *mb1 = nullptr, *vb1 = nullptr;
     float *W2 = nullptr, *mW2 = nullptr, *vW2 = nullptr;
     float *b2 = nullptr, *mb2 = nullptr, *vb2 = nullptr;
+    float *W1lo = nullptr, *W2lo = nullptr;       // W - trunc_tf32(W): rewritten by the ADAM kernel with every update
     int64_t adam_t = 0;
 
     int32_t *d_train_rows = nullptr, *d_test_rows = nullptr, *d_perm = nullptr;
@@ -73,6 +78,7 @@ struct Engine {
     // DI_MATH_TF32X3 only: residual twins a_lo = a - trunc_tf32(a) of the operands of the weight-gradient GEMMs,
     // written by the epilogue (h, dz2, dz1) or the staging gather (X) that produces the value itself
     float *Hlo = nullptr, *DZ2lo = nullptr, *DZ1lo = nullptr, *Xtr_lo = nullptr, *Xstep_lo = nullptr;
+    float *Xte_lo = nullptr, *Xchunk_lo = nullptr, *Hchunk_lo = nullptr;   // twins of the inference operands
 
     int infer_tile = 128;                         // cells per CTA of the inference forward (UMMA N): 128 or 256
     int64_t chunk_rows = 0;                       // inference chunk (multiple of infer_tile)
@@ -141,6 +147,9 @@ bool tc_available();                // false while the tensor-core kernels are n
 bool tc_init(Engine& e);            // builds tensor maps; false + e.err on failure
 void tc_destroy(Engine& e);
 bool tc_rebind(Engine& e);          // after (re)allocation of X/Y buffers
+void tc_weights_changed(Engine& e, int s);   // di_set_weights wrote sub-network s: refresh the residual twins of W1 / W2
+const char* tc_describe(Engine& e);  // one line: which kernels / knobs this handle runs with (di_describe)
+int64_t tc_fallbacks(Engine& e);     // times the epoch graph was unavailable and the steps were issued one by one
 void tc_train_step(Engine& e, const StepArgs& a, int which_x);   // which_x: 0 = Xtr/Ytr, 1 = Xstep/Ystep
 // All optimiser steps of one epoch over the staged training matrices as ONE graph launch on e.stream (built on first
 // use, rebuilt when the split changes).  lr_t[i] = Adam's bias-corrected rate of step first_step + i.  Returns false

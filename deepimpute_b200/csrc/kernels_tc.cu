@@ -79,6 +79,7 @@ struct TcParams {
     float *Hlo, *DZ2lo, *DZ1lo;                  // TF32 residual twins of h / dz2 / dz1 (nullptr: not wanted)
     float *b1, *mb1, *vb1, *b2, *mb2, *vb2;
     float *W1, *mW1, *vW1, *W2, *mW2, *vW2;      // ADAM, direct mode: updated values go to global memory from registers
+    float *W1lo, *W2lo;                          // ADAM: residual twins W - trunc_tf32(W), rewritten with every update (nullptr: not kept)
     int adam_direct;                             // 1: registers -> st.global; 0: in place in the ring + TMA stores
     int ad_nded, ad_stride;                      // one-CTA-per-SM ADAM kernel: dedicated chunk stages, bytes per stage
     int ts_wbox, ts_acol0;                       // TS kernels: features per row of the plain weight tile; first TMEM column of the weight slabs
@@ -589,6 +590,335 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
     DI_TRACE_T0(5);
 }
 
+// ============================================================================ FWD1 / FWD2 / BWD, every operand by TMA
+// LT ("lo by TMA") form of the error-compensated kernels, the default of DI_MATH_TF32X3.  The residual twin of every
+// operand already exists in HBM when the kernel starts: activations get theirs from the epilogue (h, dz2) or the
+// staging gather (X) that produces them -- the ADAM kernel needs those twins anyway -- and the weights get theirs from
+// the ADAM epilogue, which writes W_lo = W - trunc_tf32(W) next to every updated W.  A K block is then four plain TMA
+// tiles [A | A_lo | B | B_lo] and twelve MMAs; nobody touches the slabs between TMA and the tensor core, so the
+// converter warps of tc_kernel<.., true> (1250 cycles per K block, profiles/traces/r01i) and their tensor-memory
+// staging are gone and the K loop runs at the pace of the MMAs.  All sixteen non-producer warps belong to the epilogue:
+// four per TMEM lane quadrant, each a quarter of the batch columns.
+// Warp roles (576 threads): warps 0-15 epilogue, warp 16 TMA producer, warp 17 MMA issuer.
+// Split K (gridDim.x = KS > 1, launched as a cluster of KS CTAs along x): CTA x accumulates K blocks
+// [x nkb / KS, (x + 1) nkb / KS); CTAs x > 0 then add their accumulators into the shared memory of CTA 0 of the
+// cluster (distributed shared memory, fixed order: the sum is reproducible), which runs the epilogue.
+constexpr int LT_EPI_WARPS = 16;
+constexpr int LT_THREADS = (LT_EPI_WARPS + 2) * 32;
+constexpr int LT_MAX_STAGES = 6;
+
+struct LtMaps { CUtensorMap A, Alo, B, Blo, C; };
+
+template <int OP>
+__global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_constant__ LtMaps maps, const TcParams p) {
+    constexpr bool A_MN = (OP != TC_BWD);
+
+    const int s = blockIdx.z + p.s_base;
+    const SubnetDesc d = p.desc[s];
+    const int m_tile = (int)(blockIdx.y % p.m_tiles);
+    const int row_tile = (int)(blockIdx.y / p.m_tiles);
+    const int m0 = m_tile * TILE_M;
+    const int64_t row0 = p.row0 + (int64_t)row_tile * p.rows_per_block_y;
+
+    int out_dim, nkb_all;
+    int a_c0, a_c1, b_c0, b_c1, c_c0 = 0;
+    if constexpr (OP == TC_FWD1) {
+        out_dim = p.Hp; nkb_all = d.Pp / BLOCK_K;
+        a_c0 = m0; a_c1 = (int)d.coff;
+        b_c0 = (int)d.coff; b_c1 = (int)row0;
+    } else if constexpr (OP == TC_FWD2) {
+        out_dim = p.Op; nkb_all = p.Hp / BLOCK_K;
+        a_c0 = m0; a_c1 = s * p.Hp;
+        b_c0 = s * p.Hp; b_c1 = (int)row0;
+        c_c0 = s * p.Op + m0;
+    } else {
+        out_dim = p.Hp; nkb_all = p.Op / BLOCK_K;
+        a_c0 = 0; a_c1 = s * p.Hp + m0;
+        b_c0 = s * p.Op; b_c1 = 0;
+        c_c0 = s * p.Hp + m0;
+    }
+    if (m0 >= out_dim) return;                            // whole tile is padding (uniform per CTA and per cluster)
+    // split K: this CTA's share of the K blocks
+    const int ks = (int)gridDim.x, kx = (int)blockIdx.x;
+    const int kb_begin = (int)((int64_t)nkb_all * kx / ks), kb_end = (int)((int64_t)nkb_all * (kx + 1) / ks);
+    const int nkb = kb_end - kb_begin;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t b_bytes = (uint32_t)p.n_cols * BLOCK_K * 4;
+    const uint32_t stage_bytes = 2 * A_STAGE_BYTES + 2 * b_bytes;          // [A | A_lo | B | B_lo]
+    const int stages = p.stages;
+    const float* aux = reinterpret_cast<const float*>(smem + (size_t)stages * stage_bytes);
+    // after the main loop the ring is dead: its first bytes hold the partial bias-gradient sums of the epilogue
+    // (3 x 128 floats); split K: the partial accumulators of the other CTAs of the cluster follow at +2 KB
+    float* gpart = reinterpret_cast<float*>(smem);
+    __shared__ uint64_t full_bar[LT_MAX_STAGES], empty_bar[LT_MAX_STAGES], tmem_full_bar, aux_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ double red[LT_EPI_WARPS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DI_TRACE_T0(0);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        mbar_init(&aux_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == LT_EPI_WARPS && lane == 0) {
+        prefetch_tensormap(&maps.A); prefetch_tensormap(&maps.Alo); prefetch_tensormap(&maps.B); prefetch_tensormap(&maps.Blo);
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    if (warp != LT_EPI_WARPS) pdl_wait();                 // the producer waits later: see below
+    DI_TRACE_T0(1);
+
+    if (warp == LT_EPI_WARPS) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            auto load_a = [&](int kb, int st) {
+                uint8_t* sa = smem + (size_t)st * stage_bytes;
+                const int k = (kb_begin + kb) * BLOCK_K;
+                if constexpr (A_MN) {
+                    load_stage<true>(sa, &maps.A, &full_bar[st], a_c0, a_c1 + k, TILE_M);
+                    load_stage<true>(sa + A_STAGE_BYTES, &maps.Alo, &full_bar[st], a_c0, a_c1 + k, TILE_M);
+                } else {
+                    tma_load_2d(sa, &maps.A, &full_bar[st], a_c0 + k, a_c1);
+                    tma_load_2d(sa + A_STAGE_BYTES, &maps.Alo, &full_bar[st], a_c0 + k, a_c1);
+                }
+            };
+            auto load_b = [&](int kb, int st) {
+                uint8_t* sb = smem + (size_t)st * stage_bytes + 2 * A_STAGE_BYTES;
+                const int k = (kb_begin + kb) * BLOCK_K;
+                tma_load_2d(sb, &maps.B, &full_bar[st], b_c0 + k, b_c1);
+                tma_load_2d(sb + b_bytes, &maps.Blo, &full_bar[st], b_c0 + k, b_c1);
+            };
+            auto load_aux = [&]() {
+                mbar_arrive_expect_tx(&aux_bar, (uint32_t)(p.n_cols * p.aux_cols * 4));
+                tma_load_2d((void*)aux, &maps.C, &aux_bar, c_c0, (int32_t)p.aux_row0);
+            };
+            // what the grid ahead in the step's chain does NOT write is fetched before waiting for it: FWD1 follows
+            // ADAM (writes W1 / W1_lo, not the staged batch); FWD2 follows FWD1 (writes h / h_lo, not W2 or the Y
+            // tile); BWD follows FWD2 (writes dz2 / dz2_lo, not W2 or the h tile)
+            constexpr bool A_FIRST = (OP != TC_FWD1);
+            const bool want_aux = p.aux_cols > 0 && kx == 0;
+            const int npre = p.pdl_prefetch ? min(stages, nkb) : 0;
+            for (int kb = 0; kb < npre; ++kb) {
+                mbar_arrive_expect_tx(&full_bar[kb], stage_bytes);
+                if (kb < 40) DI_TRACE(8 + kb);
+                if constexpr (A_FIRST) load_a(kb, kb); else load_b(kb, kb);
+            }
+            if (npre && want_aux) load_aux();
+            pdl_wait();
+            for (int kb = 0; kb < npre; ++kb) {
+                if constexpr (A_FIRST) load_b(kb, kb); else load_a(kb, kb);
+            }
+            for (int kb = npre; kb < nkb; ++kb) {
+                const int st = kb % stages;
+                if (kb >= stages) mbar_wait(&empty_bar[st], ((kb / stages) - 1) & 1, 2);
+                if (kb < 40) DI_TRACE(8 + kb);
+                mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
+                load_a(kb, st);
+                load_b(kb, st);
+                if (kb == 0 && want_aux) load_aux();
+            }
+            if (nkb == 0 && !npre && want_aux) load_aux();
+        }
+    } else if (warp == LT_EPI_WARPS + 1) {
+        // ===== MMA issuer: per K step a_lo b + a b_lo + a b (small terms first) =====
+        if (elect_one()) {
+            const uint32_t idesc = idesc_for(p.n_cols, A_MN, false);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % stages;
+                mbar_wait(&full_bar[st], (kb / stages) & 1, 3);
+                tc_fence_after();
+                if (kb < 40) DI_TRACE(48 + kb);
+                const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                const uint32_t sa_lo = sa + A_STAGE_BYTES, sb = sa + 2 * A_STAGE_BYTES, sb_lo = sb + b_bytes;
+#pragma unroll
+                for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
+                    umma_tf32(tmem, stage_desc<A_MN>(sa_lo, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                    umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb_lo, j), idesc, 1u);
+                    umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, 1u);
+                }
+                umma_commit(&empty_bar[st]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        // ===== epilogue: warp -> TMEM lane quadrant (warp % 4) and column group (warp / 4) =====
+        const int quad = warp & 3, cg = warp >> 2;
+        const int fl = quad * 32 + lane;
+        const int f = m0 + fl;
+        const bool f_ok = f < out_dim;
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16);
+        const int ncol = p.n_cols;
+        const int cpg = ((ncol + 63) / 64) * 16;          // columns per group: a multiple of 16 (tcgen05.ld.x16)
+        const int c_lo = min(ncol, cg * cpg), c_hi = min(ncol, c_lo + cpg);
+        const bool first = cg == 0;                       // this group finishes the per-feature sums
+        const int64_t bias_i = (int64_t)s * ((OP == TC_FWD2) ? p.Op : p.Hp) + f;
+        float bias = 0.f, bw = 0.f, bm = 0.f, bv = 0.f;
+        if (f_ok) {
+            if constexpr (OP == TC_FWD1) bias = p.b1[bias_i];
+            if constexpr (OP == TC_FWD2) bias = p.b2[bias_i];
+            if (p.training && first) {
+                if constexpr (OP == TC_FWD2) { bw = bias; bm = p.mb2[bias_i]; bv = p.vb2[bias_i]; }
+                if constexpr (OP == TC_BWD) { bw = p.b1[bias_i]; bm = p.mb1[bias_i]; bv = p.vb1[bias_i]; }
+            }
+        }
+        const AdamParams adam_b = adam_of(p);
+        const uint32_t dstep = (OP == TC_FWD1) ? dropout_step(p) : 0u;
+        if (p.aux_cols > 0) mbar_wait(&aux_bar, 0, 5);
+        DI_TRACE_T0(2);
+        if (nkb > 0) mbar_wait(&tmem_full_bar, 0, 4);
+        tc_fence_after();
+        if (threadIdx.x == 0) pdl_release();
+        __syncwarp();
+        DI_TRACE_T0(3);
+
+        if constexpr (OP == TC_FWD1) {
+            const bool drop = p.training && p.drop_thresh;
+            float* hrow = p.Hact + row0 * p.ldh + (int64_t)s * p.Hp + f;
+            float* hlo = p.Hlo ? p.Hlo + row0 * p.ldh + (int64_t)s * p.Hp + f : nullptr;
+            for (int c = c_lo; c < c_hi; c += 16) {
+                float v[16];
+                __syncwarp();
+                tmem_ld16(taddr + c, v);
+                if (!f_ok) continue;
+                uint32_t w[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0xFFFFFFFFu;
+                    if (drop) dropout_words((uint32_t)f, (uint32_t)((c >> 2) + q), (uint32_t)d.gid, dstep, p.seed, w[q]);
+                }
+                float a[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    a[i] = fmaxf(v[i] + bias, 0.f);
+                    if (drop) a[i] = (w[i >> 2][i & 3] >= p.drop_thresh) ? a[i] * p.keep_scale : 0.f;
+                }
+                float* dst = hrow + (int64_t)c * p.ldh;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[(int64_t)i * p.ldh] = a[i];
+                if (hlo) {
+                    float* dlo = hlo + (int64_t)c * p.ldh;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) dlo[(int64_t)i * p.ldh] = tf32_residual(a[i]);
+                }
+            }
+        } else if constexpr (OP == TC_FWD2) {
+            const int64_t bi = bias_i;
+            float part = 0.f, gsum = 0.f;
+            const int rows_left = p.n_valid - row_tile * ncol;
+            for (int c = c_lo; c < c_hi; c += 16) {
+                float v[16], y[16];
+                __syncwarp();
+                tmem_ld16(taddr + c, v);
+                if (!f_ok) continue;
+                if (p.aux_cols > 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = aux[(c + i) * p.aux_cols + fl];
+                } else if (p.Y) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = __ldg(p.Y + (row0 + c + i) * p.ldy + bi);
+                }
+                float yh[16], sg[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) softplus_sigmoid(v[i] + bias, yh[i], sg[i]);
+                if (p.out && f < p.O) {
+                    float* dst = p.out + ((int64_t)row_tile * ncol + c) * p.ld_out + (int64_t)s * p.O + f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c + i < rows_left) dst[(int64_t)i * p.ld_out] = yh[i];
+                }
+                if (p.Y) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { const float diff = y[i] - yh[i]; part += y[i] * diff * diff; }
+                    if (p.training) {
+                        float g[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { g[i] = 2.0f * y[i] * (yh[i] - y[i]) * sg[i] * p.inv_norm; gsum += g[i]; }
+                        const int64_t ld2 = (int64_t)p.S * p.Op;
+                        float* dst = p.DZ2 + (int64_t)c * ld2 + bi;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dst[(int64_t)i * ld2] = g[i];
+                        if (p.DZ2lo) {
+                            float* dlo = p.DZ2lo + (int64_t)c * ld2 + bi;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) dlo[(int64_t)i * ld2] = tf32_residual(g[i]);
+                        }
+                    }
+                }
+            }
+            if (p.training || p.loss) {
+                double dpart = (double)part;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) dpart += __shfl_xor_sync(0xffffffffu, dpart, off);
+                if (lane == 0) red[warp] = dpart;
+                if (!first) gpart[(cg - 1) * TILE_M + fl] = gsum;
+                named_bar_sync(1, LT_EPI_WARPS * 32);
+                if (first) {
+                    gsum += gpart[fl] + gpart[TILE_M + fl] + gpart[2 * TILE_M + fl];
+                    if (p.training && f_ok) {
+                        adam_update_fast(gsum, bw, bm, bv, adam_b);
+                        p.b2[bi] = bw; p.mb2[bi] = bm; p.vb2[bi] = bv;
+                    }
+                    if (p.loss && threadIdx.x == 0) {
+                        double tot = 0.0;
+#pragma unroll
+                        for (int i = 0; i < LT_EPI_WARPS; ++i) tot += red[i];
+                        atomicAdd(p.loss, tot);
+                    }
+                }
+            }
+        } else {
+            const int64_t bi = bias_i;
+            float gsum = 0.f;
+            for (int c = c_lo; c < c_hi; c += 16) {
+                float v[16], h[16];
+                __syncwarp();
+                tmem_ld16(taddr + c, v);
+                if (!f_ok) continue;
+                if (p.aux_cols > 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) h[i] = aux[(c + i) * p.aux_cols + fl];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) h[i] = p.Hact[(int64_t)(c + i) * p.S * p.Hp + bi];
+                }
+                float g[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { g[i] = (h[i] > 0.f) ? v[i] * p.keep_scale : 0.f; gsum += g[i]; }
+                const int64_t ld1 = (int64_t)p.S * p.Hp;
+                float* dst = p.DZ1 + (int64_t)c * ld1 + bi;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[(int64_t)i * ld1] = g[i];
+                if (p.DZ1lo) {
+                    float* dlo = p.DZ1lo + (int64_t)c * ld1 + bi;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) dlo[(int64_t)i * ld1] = tf32_residual(g[i]);
+                }
+            }
+            if (!first) gpart[(cg - 1) * TILE_M + fl] = gsum;
+            named_bar_sync(1, LT_EPI_WARPS * 32);
+            if (first && f_ok) {
+                gsum += gpart[fl] + gpart[TILE_M + fl] + gpart[2 * TILE_M + fl];
+                adam_update_fast(gsum, bw, bm, bv, adam_b);
+                p.b1[bi] = bw; p.mb1[bi] = bm; p.vb1[bi] = bv;
+            }
+        }
+    }
+
+    DI_TRACE_T0(4);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+    DI_TRACE_T0(5);
+}
+
 // ============================================================================================ ADAM (weight update)
 // One CTA: dW tile [128 output features (lanes)] x [n_cols input features (columns)] = dout^T in, K = padded batch.
 // shared memory: operands (all K blocks at once) | ring of AD_STAGES x {w, m, v} x [AD_R rows][wbox floats]
@@ -783,8 +1113,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
                         gm[(int64_t)r * out_dim] = m[r];
                         gv[(int64_t)r * out_dim] = v[r];
                     }
+                    if (float* gl0 = second ? p.W2lo : p.W1lo) {
+                        float* gl = gl0 + off;
+#pragma unroll
+                        for (int r = 0; r < AD_R; ++r) gl[(int64_t)r * out_dim] = tf32_residual(w[r]);
+                    }
                     if (c < 40 && threadIdx.x == 0) DI_TRACE(48 + c);
                     continue;
+                }
+                if (float* gl0 = second ? p.W2lo : p.W1lo) {
+                    float* gl = gl0 + (row_base + n0 + (int64_t)c * AD_R) * out_dim + m0 + fl;
+#pragma unroll
+                    for (int r = 0; r < AD_R; ++r) gl[(int64_t)r * out_dim] = tf32_residual(w[r]);
                 }
 #pragma unroll
                 for (int r = 0; r < AD_R; ++r) {
@@ -813,7 +1153,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
 template <int WBOX, int LD>
 __device__ __forceinline__ void adam_chunk(uint32_t base, const float (&g)[AD_R], const AdamParams& adam,
                                            float* __restrict__ gw, float* __restrict__ gm, float* __restrict__ gv,
-                                           int wbox_rt, int ld_rt) {
+                                           float* __restrict__ gl, int wbox_rt, int ld_rt) {
     const uint32_t row_b = (WBOX > 0 ? (uint32_t)WBOX : (uint32_t)wbox_rt) * 4u;
     const uint32_t tile_b = row_b * AD_R;
     const int64_t ld = LD > 0 ? (int64_t)LD : (int64_t)ld_rt;
@@ -831,6 +1171,10 @@ __device__ __forceinline__ void adam_chunk(uint32_t base, const float (&g)[AD_R]
         gw[r * ld] = w[r];
         gm[r * ld] = m[r];
         gv[r * ld] = v[r];
+    }
+    if (gl) {                                             // residual twin of the new weights (operand of the LT kernels)
+#pragma unroll
+        for (int r = 0; r < AD_R; ++r) gl[r * ld] = tf32_residual(w[r]);
     }
 }
 
@@ -995,6 +1339,7 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
         float* gw0 = second ? p.W2 : p.W1;
         float* gm0 = second ? p.mW2 : p.mW1;
         float* gv0 = second ? p.vW2 : p.vW1;
+        float* gl0 = second ? p.W2lo : p.W1lo;
         for (int c = grp; c < nchunks; c += ngroups) {
             float g[AD_R];
             __syncwarp();
@@ -1008,10 +1353,11 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
                 // the epilogue is instruction-bound: with the row pitch known at compile time (the default topology:
                 // 128-wide tiles of W1 [.., 256] and W2 [.., 512]) every shared load and global store addresses
                 // base + immediate instead of computing 48 addresses per chunk
-                if (p.ad_generic) adam_chunk<0, 0>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, wbox, out_dim);
-                else if (wbox == TILE_M && out_dim == 256) adam_chunk<TILE_M, 256>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, 0, 0);
-                else if (wbox == TILE_M && out_dim == 512) adam_chunk<TILE_M, 512>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, 0, 0);
-                else adam_chunk<0, 0>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, wbox, out_dim);
+                float* gl = gl0 ? gl0 + off : nullptr;
+                if (p.ad_generic) adam_chunk<0, 0>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, gl, wbox, out_dim);
+                else if (wbox == TILE_M && out_dim == 256) adam_chunk<TILE_M, 256>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, gl, 0, 0);
+                else if (wbox == TILE_M && out_dim == 512) adam_chunk<TILE_M, 512>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, gl, 0, 0);
+                else adam_chunk<0, 0>(base, g, adam, gw0 + off, gm0 + off, gv0 + off, gl, wbox, out_dim);
             }
             if (tracer && c < 40) p.trace[48 + c] = clock64();
         }
@@ -1039,6 +1385,14 @@ struct TcState {
     CUtensorMap Xstep_k, Xstep_mn, Ystep_aux;
     CUtensorMap Xchunk_k, Hchunk_k;                        // inference chunk
     CUtensorMap W1_t[3], W2_t[3];                          // {w, m, v} tiles of the ADAM epilogue
+    // LT kernels (every operand by TMA): residual twins of the weights and K-major views of the activation twins
+    bool lt = false;                                       // DEEPIMPUTE_B200_LT=0 selects the converter-warp kernels
+    CUtensorMap W1lo_mn, W2lo_mn, W2lo_k, Hlo_k, DZ2lo_k, Xstep_lo_k, Xtr_lo_k, Xte_lo_k, Xchunk_lo_k, Hchunk_lo_k;
+    struct LtCfg { int stages = 0, smem = 0; bool aux = false; };
+    LtCfg lt_train, lt_train_noaux, lt_infer;
+    // L2 residency of the optimiser state (DEEPIMPUTE_B200_L2_PERSIST): access-policy window of the training launches
+    bool l2_window = false;
+    cudaAccessPolicyWindow l2_policy = {};
     // staged train / test matrices (rebuilt by tc_rebind)
     CUtensorMap Xtr_k, Xtr_mn, Xte_k, Ytr_aux;
     bool have_split = false;
@@ -1057,6 +1411,7 @@ struct TcState {
     uint32_t* d_step_base = nullptr;
     float* d_lr_table = nullptr;
     bool use_graph = true, graph_failed = false;
+    int64_t graph_fallbacks = 0;                           // epochs that ran step by step because the graph could not be built
     unsigned long long* d_trace = nullptr;                 // DEEPIMPUTE_B200_TRACE=1: 3 kernels x 256 slots
     int smem_adam = 0;
     bool x3 = false;                                       // forward GEMMs error-compensated (DI_MATH_TF32X3)
@@ -1113,14 +1468,25 @@ TcParams base_params(Engine& e) {
 }
 
 // kernel launch with or without the programmatic-stream-serialization attribute (see pdl_wait)
+const cudaAccessPolicyWindow* g_launch_window = nullptr;   // set around the training launches of an engine that keeps its state in L2
+
 template <typename... KArgs, typename... Args>
 void launch_k(void (*kernel)(KArgs...), dim3 grid, int threads, int smem, cudaStream_t stream, bool pdl, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (g_launch_window) {
+        attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[na].val.accessPolicyWindow = *g_launch_window;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = (unsigned)na;
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -1175,6 +1541,15 @@ bool tc_init(Engine& e) {
         ok = ok && make_map_2d(&st->DZ2lo_mn, e.DZ2lo, e.Bp, SO, SO, 32, true);
         ok = ok && make_map_2d(&st->DZ1lo_mn, e.DZ1lo, e.Bp, SH, SH, 32, true);
         ok = ok && make_map_2d(&st->Xstep_lo_mn, e.Xstep_lo, e.Bp, e.PT, e.PT, 32, true);
+        // LT kernels: twins of the weights (same views as W1_mn / W2_mn / W2_k) and K-major views of the activation twins
+        ok = ok && make_map_2d(&st->W1lo_mn, e.W1lo, e.PT, e.Hp, e.Hp, 32, true);
+        ok = ok && make_map_2d(&st->W2lo_mn, e.W2lo, SH, e.Op, e.Op, 32, true);
+        ok = ok && make_map_2d(&st->W2lo_k, e.W2lo, SH, e.Op, e.Op, TILE_M);
+        ok = ok && make_map_2d(&st->Hlo_k, e.Hlo, e.Bp, SH, SH, e.Bp);
+        ok = ok && make_map_2d(&st->DZ2lo_k, e.DZ2lo, e.Bp, SO, SO, e.Bp);
+        ok = ok && make_map_2d(&st->Xstep_lo_k, e.Xstep_lo, e.Bp, e.PT, e.PT, e.Bp);
+        ok = ok && make_map_2d(&st->Xchunk_lo_k, e.Xchunk_lo, e.chunk_rows, e.PT, e.PT, e.infer_tile);
+        ok = ok && make_map_2d(&st->Hchunk_lo_k, e.Hchunk_lo, e.chunk_rows, SH, SH, e.infer_tile);
     }
     ok = ok && make_map_2d(&st->Xchunk_k, e.Xchunk, e.chunk_rows, e.PT, e.PT, e.infer_tile);
     ok = ok && make_map_2d(&st->Hchunk_k, e.Hchunk, e.chunk_rows, SH, SH, e.infer_tile);
@@ -1230,6 +1605,47 @@ bool tc_init(Engine& e) {
         if (const char* v = getenv("DEEPIMPUTE_B200_TS_BWD")) st->ts_bwd = st->ts && atoi(v) != 0;
     } else {
         st->ts = false;                // the TS kernels are instantiated for the compensated mode only
+    }
+    // LT kernels: ring of [A | A_lo | B | B_lo] slabs (+ the epilogue's side tile when at least three slabs still fit)
+    if (st->x3) {
+        st->lt = !st->simt_adam;
+        if (const char* v = getenv("DEEPIMPUTE_B200_LT")) st->lt = st->lt && atoi(v) != 0;
+        auto lt_cfg = [&](int n_cols, int aux_fl) {
+            TcState::LtCfg c;
+            const int stage = 2 * (int)A_STAGE_BYTES + 2 * n_cols * BLOCK_K * 4;
+            const int room = 227 * 1024 - 1024 - 2048 - aux_fl * 4;      // alignment slack, static shared memory (cuobjdump: 2048)
+            c.stages = std::min(LT_MAX_STAGES, room / stage);
+            c.aux = aux_fl > 0;
+            c.smem = c.stages * stage + aux_fl * 4 + 1024;
+            return c;
+        };
+        st->lt_train = lt_cfg(e.Bp, aux_floats);
+        st->lt_train_noaux = lt_cfg(e.Bp, 0);
+        if (st->lt_train.stages < 3) st->lt_train = st->lt_train_noaux;
+        st->lt_infer = lt_cfg(e.infer_tile, 0);
+        if (st->lt_train.stages < 2 || st->lt_infer.stages < 2) st->lt = false;
+    }
+    // L2 residency of the optimiser state: one access-policy window over the state slab.  The persisting share of L2
+    // is a device-wide limit; hitRatio = (persisting bytes / window bytes) makes that fraction of the slab's lines
+    // stay put while the rest streams, instead of every line evicting another one step before it is needed again.
+    {
+        int want = 1;
+        if (const char* v = getenv("DEEPIMPUTE_B200_L2_PERSIST")) want = atoi(v);
+        cudaDeviceProp prop{};
+        if (want && e.state_slab && cudaGetDeviceProperties(&prop, e.cfg.device) == cudaSuccess &&
+            prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            size_t persist = (size_t)prop.persistingL2CacheMaxSize;
+            if (want > 1) persist = std::min(persist, (size_t)want << 20);           // value > 1: cap in MiB
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+                const size_t window = std::min(e.state_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+                st->l2_policy.base_ptr = e.state_slab;
+                st->l2_policy.num_bytes = window;
+                st->l2_policy.hitRatio = (float)std::min(1.0, (double)persist / (double)window);
+                st->l2_policy.hitProp = cudaAccessPropertyPersisting;
+                st->l2_policy.missProp = cudaAccessPropertyStreaming;
+                st->l2_window = true;
+            } else cudaGetLastError();
+        }
     }
     // sub-network groups of the epoch graph: independent chains on their own streams
     int G = std::min(16, e.S);
@@ -1288,6 +1704,12 @@ bool tc_init(Engine& e) {
         set((const void*)tc_kernel<TC_FWD2, true, true>, st->ts_smem2);
         if (st->ts_bwd) set((const void*)tc_kernel<TC_BWD, true, true>, st->ts_smem2);
     }
+    if (st->lt) {
+        const int ml = std::max(std::max(st->lt_train.smem, st->lt_train_noaux.smem), st->lt_infer.smem);
+        set((const void*)tc_lt_kernel<TC_FWD1>, ml);
+        set((const void*)tc_lt_kernel<TC_FWD2>, ml);
+        set((const void*)tc_lt_kernel<TC_BWD>, ml);
+    }
     set((const void*)tc_adam_kernel<false>, st->smem_adam);
     set((const void*)tc_adam_kernel<true>, st->smem_adam);
     if (st->adam_big) {
@@ -1323,6 +1745,8 @@ bool tc_rebind(Engine& e) {
     ok = ok && make_map_2d(&st->Xtr_k, e.Xtr, e.n_train_pad, e.PT, e.PT, e.Bp);
     ok = ok && make_map_2d(&st->Xtr_mn, e.Xtr, e.n_train_pad, e.PT, e.PT, 32, true);
     if (e.Xtr_lo) ok = ok && make_map_2d(&st->Xtr_lo_mn, e.Xtr_lo, e.n_train_pad, e.PT, e.PT, 32, true);
+    if (e.Xtr_lo) ok = ok && make_map_2d(&st->Xtr_lo_k, e.Xtr_lo, e.n_train_pad, e.PT, e.PT, e.Bp);
+    if (e.Xte_lo) ok = ok && make_map_2d(&st->Xte_lo_k, e.Xte_lo, e.n_test_pad, e.PT, e.PT, e.infer_tile);
     ok = ok && make_map_plain(&st->Ytr_aux, e.Ytr, e.n_train_pad, SO, SO, st->aux_y, e.Bp);
     ok = ok && make_map_2d(&st->Xte_k, e.Xte, e.n_test_pad, e.PT, e.PT, e.infer_tile);
     st->have_split = ok;
@@ -1354,7 +1778,22 @@ void launch_on(Engine& e, const StepPlan& pl, const char* name, const CUtensorMa
     count_launch(e, name);
 }
 
+template <int OP>
+void launch_lt(Engine& e, const StepPlan& pl, const char* name, const LtMaps& m, const TcParams& p, dim3 grid, int smem) {
+    const bool pdl = static_cast<TcState*>(e.tc)->pdl;
+    if (pl.graph) { launch_k(tc_lt_kernel<OP>, grid, LT_THREADS, smem, pl.main, pdl, m, p); return; }
+    KernelTimer t(e, name);
+    launch_k(tc_lt_kernel<OP>, grid, LT_THREADS, smem, pl.main, false, m, p);
+    count_launch(e, name);
+}
+
+struct WindowScope {    // training launches of an engine whose optimiser state is pinned in L2 carry its access-policy window
+    explicit WindowScope(TcState* st) { g_launch_window = st->l2_window ? &st->l2_policy : nullptr; }
+    ~WindowScope() { g_launch_window = nullptr; }
+};
+
 void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const StepPlan& pl) {
+    WindowScope window(st);
     const CUtensorMap& Xk = which_x == 0 ? st->Xtr_k : st->Xstep_k;
     const CUtensorMap& Yaux = which_x == 0 ? st->Ytr_aux : st->Ystep_aux;
     TcParams p = base_params(e);
@@ -1376,6 +1815,26 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     const TcState::Cfg& c2 = st->fwd2_train[pl.deep];
     const TcState::Cfg& c3 = st->bwd_train[pl.deep];
 
+    if (st->lt) {
+        // every operand by TMA: [W | W_lo | act | act_lo] slabs, twelve MMAs per K block, sixteen epilogue warps
+        const TcState::LtCfg& ca = st->lt_train;          // with the epilogue's side tile when it fits
+        const TcState::LtCfg& cn = st->lt_train_noaux;
+        LtMaps m;
+        { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh; q.Hlo = e.Hlo - a.row0 * q.ldh;
+          q.stages = cn.stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace;
+          m.A = st->W1_mn; m.Alo = st->W1lo_mn; m.B = Xk; m.Blo = which_x == 0 ? st->Xtr_lo_k : st->Xstep_lo_k; m.C = Xk;
+          launch_lt<TC_FWD1>(e, pl, "fwd1", m, q, dim3(1, mh, pl.ns), cn.smem); }
+        { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
+          q.stages = ca.stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 256;
+          if (ca.aux) { q.aux_cols = st->aux_y; q.aux_row0 = a.row0; }
+          m.A = st->W2_mn; m.Alo = st->W2lo_mn; m.B = st->H_k; m.Blo = st->Hlo_k; m.C = Yaux;
+          launch_lt<TC_FWD2>(e, pl, "fwd2", m, q, dim3(1, mo, pl.ns), ca.smem); }
+        { TcParams q = p; q.m_tiles = mh; q.row0 = 0;
+          q.stages = ca.stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 512;
+          if (ca.aux) { q.aux_cols = st->aux_h; q.aux_row0 = 0; }
+          m.A = st->W2_k; m.Alo = st->W2lo_k; m.B = st->DZ2_k; m.Blo = st->DZ2lo_k; m.C = st->H_aux;
+          launch_lt<TC_BWD>(e, pl, "bwd", m, q, dim3(1, mh, pl.ns), ca.smem); }
+    } else {
     { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
       q.stages = c1.stages; q.lo_stages = c1.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace;
       if (st->ts) {
@@ -1401,11 +1860,13 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
           launch_on<TC_BWD, true, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), st->ts_smem2);
       } else if (st->x3) launch_on<TC_BWD, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem);
       else launch_on<TC_BWD, false>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem); }
+    }
     if (st->simt_adam && !pl.graph) { simt_adam_only(e, a); return; }
     TcParams q = p;
     q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;
     q.row0 = a.row0; q.wbox = st->wbox1; q.wbox2 = st->wbox2;
     q.W1 = e.W1; q.mW1 = e.mW1; q.vW1 = e.vW1; q.W2 = e.W2; q.mW2 = e.mW2; q.vW2 = e.vW2;
+    q.W1lo = st->lt ? e.W1lo : nullptr; q.W2lo = st->lt ? e.W2lo : nullptr;
     q.adam_direct = st->adam_direct ? 1 : 0;
     if (!pl.graph && st->d_trace) q.trace = st->d_trace + 768;
     int maxPp = 0;
@@ -1524,7 +1985,15 @@ bool tc_train_epoch_graph(Engine& e, int64_t first_step, const float* lr_t, int6
     auto* st = static_cast<TcState*>(e.tc);
     if (!st || !st->use_graph || st->simt_adam) return false;
     if (!st->epoch_exec || st->graph_n_train != e.n_train) {
-        if (st->graph_failed || !build_epoch_graph(e, st)) { st->graph_failed = true; return false; }
+        if (st->graph_failed || !build_epoch_graph(e, st)) {
+            // not silent: the first failure is reported on stderr, every epoch that runs step by step is counted
+            // (di_graph_fallbacks, the bench line's "graph_fallbacks")
+            if (!st->graph_failed)
+                fprintf(stderr, "deepimpute_b200: the epoch graph could not be built (%s); epochs run step by step from now on\n",
+                        cudaGetErrorString(cudaPeekAtLastError()));
+            st->graph_failed = true; ++st->graph_fallbacks; cudaGetLastError();
+            return false;
+        }
     }
     const uint32_t base = (uint32_t)first_step;
     if (cudaMemcpyAsync(st->d_step_base, &base, sizeof base, cudaMemcpyHostToDevice, e.stream) != cudaSuccess) return false;
@@ -1532,6 +2001,39 @@ bool tc_train_epoch_graph(Engine& e, int64_t first_step, const float* lr_t, int6
     if (cudaGraphLaunch(st->epoch_exec, e.stream) != cudaSuccess) { cudaGetLastError(); return false; }
     e.launches += st->graph_nodes;
     return true;
+}
+
+namespace {
+__global__ void residual_kernel(const float* __restrict__ w, float* __restrict__ lo, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        lo[i] = tf32_residual(w[i]);
+}
+}  // namespace
+
+void tc_weights_changed(Engine& e, int s) {
+    if (!e.W1lo || !e.W2lo) return;
+    const int64_t n1 = (int64_t)e.Pp[s] * e.Hp, o1 = e.coff[s] * e.Hp, n2 = (int64_t)e.Hp * e.Op, o2 = (int64_t)s * e.Hp * e.Op;
+    residual_kernel<<<(unsigned)std::min<int64_t>((n1 + 255) / 256, 1184), 256, 0, e.stream>>>(e.W1 + o1, e.W1lo + o1, n1);
+    residual_kernel<<<(unsigned)std::min<int64_t>((n2 + 255) / 256, 1184), 256, 0, e.stream>>>(e.W2 + o2, e.W2lo + o2, n2);
+}
+
+const char* tc_describe(Engine& e) {
+    static thread_local char buf[512];
+    auto* st = static_cast<TcState*>(e.tc);
+    if (!st) return "fp32 CUDA-core kernels";
+    snprintf(buf, sizeof buf,
+             "fwd/bwd=%s stages=%d/%d adam=%s groups=%d graph=%d pdl=%d l2_window=%d (%.1f MB of %.1f MB state, hitRatio %.2f) graph_fallbacks=%lld",
+             st->lt ? "lt" : (st->ts ? "ts" : (st->x3 ? "x3-smem" : "tf32")),
+             st->lt ? st->lt_train.stages : st->fwd1_train[1].stages, st->lt ? st->lt_infer.stages : st->infer.stages,
+             st->adam_big ? "resident" : "ring", st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0, st->l2_window ? 1 : 0,
+             st->l2_window ? st->l2_policy.num_bytes * (double)st->l2_policy.hitRatio / 1048576.0 : 0.0,
+             e.state_bytes / 1048576.0, st->l2_window ? (double)st->l2_policy.hitRatio : 0.0, (long long)st->graph_fallbacks);
+    return buf;
+}
+
+int64_t tc_fallbacks(Engine& e) {
+    auto* st = static_cast<TcState*>(e.tc);
+    return st ? st->graph_fallbacks : 0;
 }
 
 void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_valid, bool with_loss,
@@ -1545,6 +2047,24 @@ void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_va
     p.n_valid = (int)n_valid; p.training = 0; p.drop_thresh = 0;
     const int row_tiles = (int)(rows / e.infer_tile);
     const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
+    if (st->lt) {
+        const TcState::LtCfg& c = st->lt_infer;
+        LtMaps m;
+        p.stages = c.stages;
+        { TcParams q = p; q.m_tiles = mh; q.row0 = row0; q.Hact = e.Hchunk - row0 * q.ldh; q.Hlo = e.Hchunk_lo - row0 * q.ldh;
+          m.A = st->W1_mn; m.Alo = st->W1lo_mn; m.B = Xk; m.Blo = which_x == 2 ? st->Xte_lo_k : st->Xchunk_lo_k; m.C = Xk;
+          KernelTimer t(e, "infer1");
+          tc_lt_kernel<TC_FWD1><<<dim3(1, mh * row_tiles, e.S), LT_THREADS, c.smem, e.stream>>>(m, q);
+          count_launch(e, "infer1"); }
+        { TcParams q = p; q.m_tiles = mo; q.row0 = 0;
+          if (with_loss) { q.Y = e.Yte + row0 * (int64_t)e.S * e.Op; q.ldy = (int64_t)e.S * e.Op; q.loss = e.d_loss + 1; }
+          q.out = out; q.ld_out = ld_out;
+          m.A = st->W2_mn; m.Alo = st->W2lo_mn; m.B = st->Hchunk_k; m.Blo = st->Hchunk_lo_k; m.C = st->Hchunk_k;
+          KernelTimer t(e, "infer2");
+          tc_lt_kernel<TC_FWD2><<<dim3(1, mo * row_tiles, e.S), LT_THREADS, c.smem, e.stream>>>(m, q);
+          count_launch(e, "infer2"); }
+        return;
+    }
     // hidden activations of this pass live in Hchunk rows [0, rows)
     { TcParams q = p; q.m_tiles = mh; q.row0 = row0; q.Hact = e.Hchunk - row0 * q.ldh;
       if (st->x3) launch<TC_FWD1, true>(e, "infer1", st->W1_mn, Xk, Xk, q, dim3(1, mh * row_tiles, e.S), st->infer.smem);

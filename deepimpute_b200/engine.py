@@ -404,6 +404,15 @@ class Engine:
     def last_device_ms(self):
         return float(self.lib.di_last_device_ms(self._h))
 
+    def describe(self):
+        """Which kernels / knobs the handle runs with (one line) -- goes into the bench line."""
+        msg = self.lib.di_describe(self._h)
+        return msg.decode() if msg else ""
+
+    def graph_fallbacks(self):
+        """Epochs that could not be replayed as a CUDA graph and ran step by step (0 in normal operation)."""
+        return int(self.lib.di_graph_fallbacks(self._h))
+
     def set_profiling(self, on=True):
         self._check(self.lib.di_set_profiling(self._h, 1 if on else 0))
 

@@ -34,8 +34,10 @@ extern "C" {
 #define DI_MATH_FP32     0   /* CUDA-core fp32 FFMA kernels (bit-for-bit fp32 products)          */
 #define DI_MATH_TF32     1   /* tcgen05 kind::tf32 tensor-core kernels, fp32 accumulate in TMEM; operands are
                                 TRUNCATED to TF32 by the tensor core (about 1e-3 relative per product)        */
-#define DI_MATH_TF32X3   2   /* same kernels, forward GEMMs error-compensated (a_hi b_hi + a_hi b_lo + a_lo b_hi):
-                                fp32-level activations and predictions; gradient GEMMs stay single-pass TF32 */
+#define DI_MATH_TF32X3   2   /* same tensor cores, EVERY GEMM of the step error-compensated (a b ~ a_hi b_hi + a_hi b_lo +
+                                a_lo b_hi with a_hi = trunc_tf32(a), a_lo = a - a_hi): the three forward / backward GEMMs
+                                and both weight-gradient GEMMs; fp32-level products (dropped a_lo b_lo term: 2^-22).
+                                The default of the Python layer; DESIGN.md section 4 states the measured tolerance */
 
 #define DI_DTYPE_F32     0   /* element type of a count matrix / of the imputed output */
 #define DI_DTYPE_F64     1
@@ -176,6 +178,11 @@ int64_t di_kernel_launches(const di_handle* h, const char* which);
  * which = "h" [B][S*Hp], "dz2" [B][S*Op], "dz1" [B][S*Hp], or "norm" [N][G] (the resident normalised matrix);
  * *ld receives the row pitch in floats. */
 int di_debug_read(di_handle* h, const char* which, float* out, int64_t capacity_floats, int64_t* ld);
+/* One line naming the kernels and knobs this handle runs with (kernel family, ring depths, epoch graph, L2 window),
+ * valid until the next call on this thread; and how many epochs could NOT be replayed as a CUDA graph and were issued
+ * step by step instead (0 in normal operation; also reported on stderr the first time it happens). */
+const char* di_describe(di_handle* h);
+int64_t di_graph_fallbacks(di_handle* h);
 int di_version(void);
 /* 1 if this build carries kernels for the DI_MATH_* mode, else 0 (di_create then fails with DI_ERR_ARG). */
 int di_math_mode_available(int32_t math_mode);

@@ -1,0 +1,113 @@
+"""Oracle parity ON THE CONFIGURATIONS THAT ARE BENCHMARKED, in the math mode and launch mode that are benchmarked.
+
+bench.py measures BASELINE.json configs[1] (c2: 10k x 5k, 10 sub-networks) and configs[2] (c3: 50k x 20k, 40
+sub-networks) with the default engine: ``tf32x3`` products, one CUDA graph per epoch over 16 sub-network groups,
+dependent-launch chain.  The CPU oracle cannot train 40 sub-networks for an epoch in test time, but it does not have
+to: the branches of the reference's model share nothing (reference multinet.py:132-148 -- separate Input, Dense,
+Dropout, Dense per branch), so a branch trained alone follows exactly the trajectory it follows inside the full
+model.  The tests therefore
+
+  1. train the FULL model on the GPU for one epoch of the benchmarked workload (``bench.build_workload``: the very
+     matrix, partition and cell split the bench times),
+  2. train ``OracleNet(subnet_ids=[...])`` restricted to a few sampled sub-networks on the same rows, same
+     permutation, same Philox dropout stream (keyed by the GLOBAL sub-network number) on the CPU,
+  3. compare weights, validation loss contribution and predictions of those sub-networks, and
+  4. check the independence claim itself on the device: an engine that holds only the sampled sub-networks gives
+     bit-identical predictions to the full model's columns, and its loss / val_loss equal the oracle's.
+
+Tolerances (error against the scale of the compared tensor, as in test_engine_gpu.py): predictions 2e-3, weights 2e-3,
+losses 1e-3 relative -- the ``tf32x3`` row of DESIGN.md section 4.
+"""
+import numpy as np
+import pytest
+
+from deepimpute_b200.engine import Engine, epoch_permutation
+from oracle.multinet_oracle import OracleNet, stage
+
+pytestmark = pytest.mark.gpu
+
+H, O, LR, RATE, SEED = 256, 512, 1e-4, 0.2, 1234
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
+
+
+def _workload(name):
+    import os
+    import bench
+    os.environ["DI_BENCH_PREDICTORS"] = "0"       # the pinned copy of the raw counts is only for the bench's side blocks
+    wl = bench.build_workload(name, "cuda:0")
+    norm = wl["norm"].numpy()
+    return wl, norm
+
+
+def _check_sampled(name, sampled, epochs):
+    wl, norm = _workload(name)
+    B = wl["B"]
+    n_pred = [len(p) for p in wl["pred_idx"]]
+    S = len(n_pred)
+    assert max(sampled) < S
+    tr, te = wl["train_rows"], wl["test_rows"]
+    perms = [epoch_permutation(SEED, e, len(tr)) for e in range(epochs)]
+
+    # (1) the full model exactly as bench.py runs it (default math mode, epoch graph, sub-network groups)
+    full = Engine(n_pred, hidden=H, sub_outputdim=O, learning_rate=LR, batch_size=B, dropout_rate=RATE, seed=SEED)
+    assert full.math_mode == "tf32x3"
+    full.set_data(norm, wl["pred_idx"], wl["targ_idx"])
+    full.set_split(tr, te)
+    full_hist = [full.train_epoch(p) for p in perms]
+    assert full.graph_fallbacks() == 0, full.describe()
+    rows = np.random.default_rng(5).choice(wl["N"], 1500, replace=False).astype(np.int32)
+    full_pred = full.predict(rows=rows)
+    full_w = full.get_weights()
+    full.close()
+
+    # (4) the sampled sub-networks alone on the device: same trajectory, bit for bit
+    sel_pred = [wl["pred_idx"][s] for s in sampled]
+    sel_targ = np.ascontiguousarray(wl["targ_idx"][sampled])
+    sel_np = [n_pred[s] for s in sampled]
+    part = Engine(sel_np, hidden=H, sub_outputdim=O, learning_rate=LR, batch_size=B, dropout_rate=RATE, seed=SEED,
+                  subnet_ids=sampled)
+    part.set_data(norm, sel_pred, sel_targ)
+    part.set_split(tr, te)
+    part_hist = [part.train_epoch(p) for p in perms]
+    part_pred = part.predict(rows=rows)
+    part.close()
+    for k, s in enumerate(sampled):
+        np.testing.assert_array_equal(part_pred[:, k * O:(k + 1) * O], full_pred[:, s * O:(s + 1) * O])
+
+    # (2) the oracle on the sampled sub-networks
+    ref = OracleNet(sel_np, H, O, learning_rate=LR, batch_size=B, dropout_rate=RATE, seed=SEED, subnet_ids=sampled)
+    Xtr, Ytr = stage(norm, sel_pred, sel_targ, tr)
+    Xte, Yte = stage(norm, sel_pred, sel_targ, te)
+    step, ref_hist = 0, []
+    for p in perms:
+        loss, step = ref.train_epoch(Xtr, Ytr, p, step)
+        ref_hist.append((loss, ref.loss(Xte, Yte)))
+    del Xtr, Ytr
+
+    # (3) compare
+    np.testing.assert_allclose(np.asarray(part_hist), np.asarray(ref_hist), rtol=1e-3)
+    want = np.hstack(ref.forward(stage(norm, sel_pred, sel_targ, rows)[0]))
+    assert rel_err(part_pred, want) < 2e-3
+    for k, s in enumerate(sampled):
+        for got_a, ref_a in zip(full_w[s], ref.get_weights()[k]):
+            assert rel_err(got_a, ref_a) < 2e-3
+    # the full model's own losses are finite, fall, and contain the sampled part
+    fh = np.asarray(full_hist)
+    assert np.isfinite(fh).all() and (fh[:, 0] > np.asarray(part_hist)[:, 0]).all()
+    return fh
+
+
+def test_c2_sampled_subnetworks_match_oracle():
+    """configs[1]: 10k x 5k, S 10, 149 Adam steps per epoch; two epochs, sub-networks 0, 4 and 9."""
+    fh = _check_sampled("c2", [0, 4, 9], epochs=2)
+    assert fh[1, 0] < fh[0, 0]
+
+
+def test_c3_sampled_subnetworks_match_oracle():
+    """configs[2], the benchmarked configuration: 50k x 20k, S 40, 743 Adam steps per epoch; one epoch, sub-networks
+    3 and 38 (first and last sub-network groups of the epoch graph)."""
+    _check_sampled("c3", [3, 38], epochs=1)
