@@ -281,6 +281,9 @@ def main():
     ap.add_argument("--epochs", type=int, default=20, help="training epochs per step (fixed; no early stopping)")
     ap.add_argument("--math", default=None, choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-shard", default=None, metavar="R/N",
+                    help="tuning aid: on ONE GPU, train and predict only the sub-networks rank R of an N-rank run would own "
+                         "(what one GPU of an N-GPU job does, without the collectives); the line says so in config")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -333,6 +336,10 @@ def main():
     S_all = len(n_pred_all)
     owned = parallel.assign_subnets(n_pred_all, world, HIDDEN, OUT)
     mine = owned[rank]
+    if args.emulate_shard and world == 1:
+        r, n = (int(x) for x in args.emulate_shard.split("/"))
+        owned = [parallel.assign_subnets(n_pred_all, n, HIDDEN, OUT)[r]]
+        mine = owned[0]
     n_pred = [n_pred_all[s] for s in mine]
     pred_idx = [wl["pred_idx"][s] for s in mine]
     targ_idx = np.ascontiguousarray(wl["targ_idx"][mine])
@@ -475,7 +482,9 @@ def main():
                        "sub_networks": S_all, "hidden": HIDDEN, "sub_outputdim": OUT,
                        "predictors_per_subnet": [int(min(n_pred_all)), int(max(n_pred_all))],
                        "adam_steps_per_epoch": steps_per_epoch, "math_mode": math_mode,
-                       "parallelism": "sub-networks sharded over {} GPU(s)".format(world),
+                       "parallelism": "sub-networks sharded over {} GPU(s)".format(world) if not args.emulate_shard else
+                                      "EMULATION of rank {} of a sharded run on one GPU: {} of {} sub-networks, no collectives"
+                                      .format(args.emulate_shard, len(mine), S_all),
                        "epoch_driver": "one CUDA-graph launch per epoch over sub-network groups on concurrent streams; "
                                        "roofline.kernels are timed in a separate launch-by-launch epoch",
                        "l2": "inputs larger than L2: {:.1f} GB of weights+Adam state+staged batches stream per epoch"

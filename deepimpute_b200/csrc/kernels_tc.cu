@@ -80,6 +80,8 @@ struct TcParams {
     float *b1, *mb1, *vb1, *b2, *mb2, *vb2;
     float *W1, *mW1, *vW1, *W2, *mW2, *vW2;      // ADAM, direct mode: updated values go to global memory from registers
     float *W1lo, *W2lo;                          // ADAM: residual twins W - trunc_tf32(W), rewritten with every update (nullptr: not kept)
+    float* kpart;                                // LT split K: partial accumulators [S][m_tiles][KS][n_cols][128]
+    unsigned int* kcount;                        // ... and arrival counters [S][m_tiles] (zero between launches)
     int adam_direct;                             // 1: registers -> st.global; 0: in place in the ring + TMA stores
     int ad_nded, ad_stride;                      // one-CTA-per-SM ADAM kernel: dedicated chunk stages, bytes per stage
     int ts_wbox, ts_acol0;                       // TS kernels: features per row of the plain weight tile; first TMEM column of the weight slabs
@@ -600,9 +602,11 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
 // staging are gone and the K loop runs at the pace of the MMAs.  All sixteen non-producer warps belong to the epilogue:
 // four per TMEM lane quadrant, each a quarter of the batch columns.
 // Warp roles (576 threads): warps 0-15 epilogue, warp 16 TMA producer, warp 17 MMA issuer.
-// Split K (gridDim.x = KS > 1, launched as a cluster of KS CTAs along x): CTA x accumulates K blocks
-// [x nkb / KS, (x + 1) nkb / KS); CTAs x > 0 then add their accumulators into the shared memory of CTA 0 of the
-// cluster (distributed shared memory, fixed order: the sum is reproducible), which runs the epilogue.
+// Split K (gridDim.x = KS > 1; used when a GPU holds so few sub-networks that most SMs would idle while one CTA walks
+// the whole K loop): CTA x accumulates K blocks [x nkb / KS, (x + 1) nkb / KS), writes its accumulator to a scratch
+// tile in global memory (L2) and counts itself in; the CTA that arrives last adds the KS partial tiles in index order
+// -- the sum does not depend on which CTA that is -- and runs the epilogue.  Nobody waits for anybody, so the CTAs of a
+// tile need not be co-resident.
 constexpr int LT_EPI_WARPS = 16;
 constexpr int LT_THREADS = (LT_EPI_WARPS + 2) * 32;
 constexpr int LT_MAX_STAGES = 6;
@@ -653,7 +657,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
     // (3 x 128 floats); split K: the partial accumulators of the other CTAs of the cluster follow at +2 KB
     float* gpart = reinterpret_cast<float*>(smem);
     __shared__ uint64_t full_bar[LT_MAX_STAGES], empty_bar[LT_MAX_STAGES], tmem_full_bar, aux_bar;
-    __shared__ uint32_t tmem_base_slot;
+    __shared__ uint32_t tmem_base_slot, arrival_slot;
     __shared__ double red[LT_EPI_WARPS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -704,7 +708,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
             // ADAM (writes W1 / W1_lo, not the staged batch); FWD2 follows FWD1 (writes h / h_lo, not W2 or the Y
             // tile); BWD follows FWD2 (writes dz2 / dz2_lo, not W2 or the h tile)
             constexpr bool A_FIRST = (OP != TC_FWD1);
-            const bool want_aux = p.aux_cols > 0 && kx == 0;
+            const bool want_aux = p.aux_cols > 0;        // split K: any CTA of the tile may be the one that runs the epilogue
             const int npre = p.pdl_prefetch ? min(stages, nkb) : 0;
             for (int kb = 0; kb < npre; ++kb) {
                 mbar_arrive_expect_tx(&full_bar[kb], stage_bytes);
@@ -771,34 +775,82 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
         }
         const AdamParams adam_b = adam_of(p);
         const uint32_t dstep = (OP == TC_FWD1) ? dropout_step(p) : 0u;
+        // dropout keep-bits of this thread's columns: forty Philox rounds per 16 columns that depend on nothing the
+        // main loop produces, so they are drawn while the tensor core works (bit i: column c_lo + i is kept)
+        uint64_t keep = ~0ull;
+        if constexpr (OP == TC_FWD1) {
+            if (p.training && p.drop_thresh && f_ok) {
+                keep = 0ull;
+                for (int c = c_lo; c < c_hi; c += 4) {
+                    uint32_t w[4];
+                    dropout_words((uint32_t)f, (uint32_t)(c >> 2), (uint32_t)d.gid, dstep, p.seed, w);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) keep |= (uint64_t)(w[i] >= p.drop_thresh ? 1u : 0u) << (c - c_lo + i);
+                }
+            }
+        }
         if (p.aux_cols > 0) mbar_wait(&aux_bar, 0, 5);
         DI_TRACE_T0(2);
         if (nkb > 0) mbar_wait(&tmem_full_bar, 0, 4);
         tc_fence_after();
+        // split K: park this CTA's accumulator in the scratch tile, count in, and carry on only as the last arrival
+        const float* ksum = nullptr;                      // != nullptr: the epilogue sums the KS scratch tiles instead of reading TMEM
+        if (ks > 1) {
+            const int64_t tile = ((int64_t)s * p.m_tiles + m_tile) * ks;
+            float* mine = p.kpart + (tile + kx) * (int64_t)ncol * TILE_M + fl;
+            for (int c = c_lo; c < c_hi; c += 16) {
+                float v[16];
+                __syncwarp();
+                if (nkb > 0) tmem_ld16(taddr + c, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) mine[(int64_t)(c + i) * TILE_M] = nkb > 0 ? v[i] : 0.f;
+            }
+            __threadfence();
+            named_bar_sync(1, LT_EPI_WARPS * 32);
+            if (threadIdx.x == 0) {
+                unsigned int* cnt = p.kcount + (int64_t)s * p.m_tiles + m_tile;
+                const unsigned int prev = atomicAdd(cnt, 1u);
+                if (prev == (unsigned int)(ks - 1)) *cnt = 0u;     // everybody has arrived: ready for the next launch
+                arrival_slot = prev;
+                __threadfence();
+            }
+            named_bar_sync(1, LT_EPI_WARPS * 32);
+            if (arrival_slot == (unsigned int)(ks - 1)) ksum = p.kpart + tile * (int64_t)ncol * TILE_M + fl;
+        }
+        const bool run_epilogue = ks == 1 || ksum != nullptr;
         if (threadIdx.x == 0) pdl_release();
         __syncwarp();
         DI_TRACE_T0(3);
+        auto load_acc = [&](int c, float (&v)[16]) {
+            __syncwarp();
+            if (ksum) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                for (int k = 0; k < ks; ++k) {
+                    const float* src = ksum + ((int64_t)k * ncol + c) * TILE_M;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += __ldcg(src + (int64_t)i * TILE_M);
+                }
+            } else {
+                tmem_ld16(taddr + c, v);
+            }
+        };
 
-        if constexpr (OP == TC_FWD1) {
+        if (!run_epilogue) {
+            // another CTA of this tile finishes it
+        } else if constexpr (OP == TC_FWD1) {
             const bool drop = p.training && p.drop_thresh;
             float* hrow = p.Hact + row0 * p.ldh + (int64_t)s * p.Hp + f;
             float* hlo = p.Hlo ? p.Hlo + row0 * p.ldh + (int64_t)s * p.Hp + f : nullptr;
             for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16];
-                __syncwarp();
-                tmem_ld16(taddr + c, v);
+                load_acc(c, v);
                 if (!f_ok) continue;
-                uint32_t w[4][4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0xFFFFFFFFu;
-                    if (drop) dropout_words((uint32_t)f, (uint32_t)((c >> 2) + q), (uint32_t)d.gid, dstep, p.seed, w[q]);
-                }
                 float a[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     a[i] = fmaxf(v[i] + bias, 0.f);
-                    if (drop) a[i] = (w[i >> 2][i & 3] >= p.drop_thresh) ? a[i] * p.keep_scale : 0.f;
+                    if (drop) a[i] = ((keep >> (c - c_lo + i)) & 1ull) ? a[i] * p.keep_scale : 0.f;
                 }
                 float* dst = hrow + (int64_t)c * p.ldh;
 #pragma unroll
@@ -815,8 +867,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
             const int rows_left = p.n_valid - row_tile * ncol;
             for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16], y[16];
-                __syncwarp();
-                tmem_ld16(taddr + c, v);
+                load_acc(c, v);
                 if (!f_ok) continue;
                 if (p.aux_cols > 0) {
 #pragma unroll
@@ -879,8 +930,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
             float gsum = 0.f;
             for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16], h[16];
-                __syncwarp();
-                tmem_ld16(taddr + c, v);
+                load_acc(c, v);
                 if (!f_ok) continue;
                 if (p.aux_cols > 0) {
 #pragma unroll
@@ -1390,6 +1440,9 @@ struct TcState {
     CUtensorMap W1lo_mn, W2lo_mn, W2lo_k, Hlo_k, DZ2lo_k, Xstep_lo_k, Xtr_lo_k, Xte_lo_k, Xchunk_lo_k, Hchunk_lo_k;
     struct LtCfg { int stages = 0, smem = 0; bool aux = false; };
     LtCfg lt_train, lt_train_noaux, lt_infer;
+    int lt_ks = 1;                                         // split-K factor of FWD1 / BWD (1: one CTA walks the whole K loop)
+    float* kpart[2] = {nullptr, nullptr};                  // scratch tiles of FWD1 / BWD: [S][m_tiles][lt_ks][Bp][128]
+    unsigned int* kcount[2] = {nullptr, nullptr};          // arrival counters [S][m_tiles]
     // L2 residency of the optimiser state (DEEPIMPUTE_B200_L2_PERSIST): access-policy window of the training launches
     bool l2_window = false;
     cudaAccessPolicyWindow l2_policy = {};
@@ -1608,8 +1661,15 @@ bool tc_init(Engine& e) {
     }
     // LT kernels: ring of [A | A_lo | B | B_lo] slabs (+ the epilogue's side tile when at least three slabs still fit)
     if (st->x3) {
-        st->lt = !st->simt_adam;
-        if (const char* v = getenv("DEEPIMPUTE_B200_LT")) st->lt = st->lt && atoi(v) != 0;
+        // Policy.  The LT kernels read W and W_lo (8 B per weight and GEMM instead of 4) and make the ADAM kernel write
+        // W_lo: free while the optimiser state sits in the 126 MB L2, a net loss once it streams from HBM (measured on
+        // c3, 40 sub-networks, 180 MB of state: 104 us per step against 94 us with the converter-warp kernels;
+        // profiles/r02a_ab_c3.md).  So: LT when the state fits L2 -- few sub-networks per GPU, exactly where the step
+        // is bound by the latency of the kernel chain rather than by HBM -- the converter-warp kernels otherwise.
+        double max_mb = 100.0;
+        if (const char* v = getenv("DEEPIMPUTE_B200_LT_MAX_MB")) max_mb = atof(v);
+        st->lt = !st->simt_adam && (double)e.state_bytes <= max_mb * 1048576.0;
+        if (const char* v = getenv("DEEPIMPUTE_B200_LT")) st->lt = !st->simt_adam && atoi(v) != 0;
         auto lt_cfg = [&](int n_cols, int aux_fl) {
             TcState::LtCfg c;
             const int stage = 2 * (int)A_STAGE_BYTES + 2 * n_cols * BLOCK_K * 4;
@@ -1624,12 +1684,32 @@ bool tc_init(Engine& e) {
         if (st->lt_train.stages < 3) st->lt_train = st->lt_train_noaux;
         st->lt_infer = lt_cfg(e.infer_tile, 0);
         if (st->lt_train.stages < 2 || st->lt_infer.stages < 2) st->lt = false;
+        if (st->lt) {
+            // split K of FWD1 / BWD: as many CTAs per tile as idle SMs allow (at most 4), never more than K blocks
+            const int mh = (e.Hp + TILE_M - 1) / TILE_M;
+            int min_kb = e.Op / BLOCK_K;
+            for (int s = 0; s < e.S; ++s) min_kb = std::min(min_kb, e.Pp[s] / BLOCK_K);
+            st->lt_ks = std::max(1, std::min(std::min(4, min_kb), 148 / std::max(1, mh * e.S)));
+            if (const char* v = getenv("DEEPIMPUTE_B200_SPLITK")) st->lt_ks = std::max(1, std::min(std::min(8, min_kb), atoi(v)));
+            if (st->lt_ks > 1) {
+                const size_t tiles = (size_t)e.S * mh;
+                for (int k = 0; k < 2 && ok; ++k) {
+                    ok = cudaMalloc((void**)&st->kpart[k], tiles * st->lt_ks * e.Bp * TILE_M * sizeof(float)) == cudaSuccess &&
+                         cudaMalloc((void**)&st->kcount[k], tiles * sizeof(unsigned int)) == cudaSuccess &&
+                         cudaMemset(st->kcount[k], 0, tiles * sizeof(unsigned int)) == cudaSuccess;
+                }
+                if (!ok) { e.err = "split-K scratch allocation failed"; return false; }
+            }
+        }
     }
     // L2 residency of the optimiser state: one access-policy window over the state slab.  The persisting share of L2
     // is a device-wide limit; hitRatio = (persisting bytes / window bytes) makes that fraction of the slab's lines
     // stay put while the rest streams, instead of every line evicting another one step before it is needed again.
     {
-        int want = 1;
+        // Off by default: measured on c3 it is a large LOSS (2697 ms per bench step against 1561 without): the set-aside
+        // takes 79 MB of L2 away from everything that is not the state -- the staged batches, activations and the
+        // gather all slow down by more than the state's hits win back (profiles/r02a_ab_c3.md).  Kept as an experiment.
+        int want = 0;
         if (const char* v = getenv("DEEPIMPUTE_B200_L2_PERSIST")) want = atoi(v);
         cudaDeviceProp prop{};
         if (want && e.state_slab && cudaGetDeviceProperties(&prop, e.cfg.device) == cudaSuccess &&
@@ -1732,6 +1812,7 @@ void tc_destroy(Engine& e) {
         if (st->d_step_base) cudaFree(st->d_step_base);
         if (st->d_trace) cudaFree(st->d_trace);
         if (st->d_lr_table) cudaFree(st->d_lr_table);
+        for (int k = 0; k < 2; ++k) { if (st->kpart[k]) cudaFree(st->kpart[k]); if (st->kcount[k]) cudaFree(st->kcount[k]); }
     }
     delete st;
     e.tc = nullptr;
@@ -1822,8 +1903,9 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
         LtMaps m;
         { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh; q.Hlo = e.Hlo - a.row0 * q.ldh;
           q.stages = cn.stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace;
+          q.kpart = st->kpart[0]; q.kcount = st->kcount[0];
           m.A = st->W1_mn; m.Alo = st->W1lo_mn; m.B = Xk; m.Blo = which_x == 0 ? st->Xtr_lo_k : st->Xstep_lo_k; m.C = Xk;
-          launch_lt<TC_FWD1>(e, pl, "fwd1", m, q, dim3(1, mh, pl.ns), cn.smem); }
+          launch_lt<TC_FWD1>(e, pl, "fwd1", m, q, dim3(st->lt_ks, mh, pl.ns), cn.smem); }
         { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
           q.stages = ca.stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 256;
           if (ca.aux) { q.aux_cols = st->aux_y; q.aux_row0 = a.row0; }
@@ -1832,8 +1914,9 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
         { TcParams q = p; q.m_tiles = mh; q.row0 = 0;
           q.stages = ca.stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 512;
           if (ca.aux) { q.aux_cols = st->aux_h; q.aux_row0 = 0; }
+          q.kpart = st->kpart[1]; q.kcount = st->kcount[1];
           m.A = st->W2_k; m.Alo = st->W2lo_k; m.B = st->DZ2_k; m.Blo = st->DZ2lo_k; m.C = st->H_aux;
-          launch_lt<TC_BWD>(e, pl, "bwd", m, q, dim3(1, mh, pl.ns), ca.smem); }
+          launch_lt<TC_BWD>(e, pl, "bwd", m, q, dim3(st->lt_ks, mh, pl.ns), ca.smem); }
     } else {
     { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
       q.stages = c1.stages; q.lo_stages = c1.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace;
@@ -2022,8 +2105,8 @@ const char* tc_describe(Engine& e) {
     auto* st = static_cast<TcState*>(e.tc);
     if (!st) return "fp32 CUDA-core kernels";
     snprintf(buf, sizeof buf,
-             "fwd/bwd=%s stages=%d/%d adam=%s groups=%d graph=%d pdl=%d l2_window=%d (%.1f MB of %.1f MB state, hitRatio %.2f) graph_fallbacks=%lld",
-             st->lt ? "lt" : (st->ts ? "ts" : (st->x3 ? "x3-smem" : "tf32")),
+             "fwd/bwd=%s splitk=%d stages=%d/%d adam=%s groups=%d graph=%d pdl=%d l2_window=%d (%.1f MB of %.1f MB state, hitRatio %.2f) graph_fallbacks=%lld",
+             st->lt ? "lt" : (st->ts ? "ts" : (st->x3 ? "x3-smem" : "tf32")), st->lt ? st->lt_ks : 1,
              st->lt ? st->lt_train.stages : st->fwd1_train[1].stages, st->lt ? st->lt_infer.stages : st->infer.stages,
              st->adam_big ? "resident" : "ring", st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0, st->l2_window ? 1 : 0,
              st->l2_window ? st->l2_policy.num_bytes * (double)st->l2_policy.hitRatio / 1048576.0 : 0.0,

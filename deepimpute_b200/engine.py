@@ -357,10 +357,11 @@ class Engine:
             if isinstance(v, (list, tuple)):
                 arrays["extra_{}_n".format(k)] = np.asarray(len(v))
                 for i, a in enumerate(v):
-                    arrays["extra_{}_{}".format(k, i)] = np.asarray(a).astype(str)
+                    a = np.asarray(a)       # gene labels keep their type (integer column names stay integers)
+                    arrays["extra_{}_{}".format(k, i)] = a.astype(str) if a.dtype.kind in "OUS" else a
             else:
                 a = np.asarray(v)
-                arrays["extra_" + k] = a.astype(str) if a.dtype == object else a
+                arrays["extra_" + k] = a.astype(str) if a.dtype.kind in "OUS" else a
         np.savez(path, **arrays, **{"meta_" + k: np.asarray(v) for k, v in meta.items()})
 
     @staticmethod

@@ -251,6 +251,10 @@ class MultiNet:
         """Select genes, partition them into sub-networks, train all of them on the GPU, record test metrics."""
         inspect_data(raw)
 
+        if self.shard is not None and self.shard.distributed and self.seed is None:
+            # every rank derives targets / predictors / the cell split from its own np.random stream: without a shared
+            # seed the shards would silently train pieces of different models
+            raise ValueError("a sharded fit needs a seed (seed=None reseeds every rank from entropy)")
         if self.seed is not None:
             np.random.seed(self.seed)
 
@@ -275,6 +279,9 @@ class MultiNet:
             print("{} genes selected for imputation".format(len(genes)))
         else:
             user = cols.get_indexer(genes_to_impute)
+            if (user < 0).any():        # the reference fails here too (KeyError from reindex / .loc, multinet.py:213, :356)
+                missing = [g for g, u in zip(genes_to_impute, user) if u < 0]
+                raise KeyError("genes_to_impute not in the input columns: {}".format(missing[:10]))
             if len(user) % self.sub_outputdim != 0:
                 print("The number of input genes is not a multiple of {}. Filling with other genes."
                       .format(len(user)))
@@ -288,13 +295,22 @@ class MultiNet:
         self.timings["stats_engine"] = "gpu" if gpu_stats else "host"
         # the correlation matrix is O(G^2 N): float64 numpy on the host for small inputs (bit-for-bit the reference's
         # selection), the GPU (fp32, di_corr_topk) for large ones, where the host takes minutes
-        use_gpu = self.predictor_engine == "gpu" or (
-            self.predictor_engine == "auto" and n_pred is None and
-            float(len(cand)) ** 2 * raw.shape[0] >= 2e11)
+        # (di_corr_topk keeps at most 8 candidates per target; a wider ntop stays on the host.  With n_pred the device
+        # path has the working semantic of DESIGN.md section 9: rows = all targets, columns = the n_pred candidates.)
+        use_gpu = ntop <= 8 and (self.predictor_engine == "gpu" or (
+            self.predictor_engine == "auto" and float(raw.shape[1]) ** 2 * raw.shape[0] >= 2e11))
         t0 = _time.perf_counter()
         if use_gpu:
-            self._set_partition_gpu(cols, raw_values, genes, cand, ntop, mode)
-        else:
+            state = np.random.get_state()
+            try:
+                self._set_partition_gpu(cols, raw_values, genes, cand, ntop, mode)
+            except ValueError as exc:
+                # a sub-network whose targets cover every candidate: the host path warns and uses all candidates
+                # (multinet.py:351-354); take it, from the same point of the random stream
+                warnings.warn("GPU predictor selection not applicable ({}); using the host path".format(exc))
+                np.random.set_state(state)
+                use_gpu = False
+        if not use_gpu:
             corr = partition.abs_correlation(raw_values, cand)
             self._set_partition(cols, raw_values, genes, cand, corr, ntop, mode)
         self.timings["predictor_selection_s"] = _time.perf_counter() - t0

@@ -3,7 +3,7 @@
 Same flag names, types and defaults as the reference's argparse set-up (reference ``deepimpute/parser.py:3-95``),
 including its defaults that disagree with its own help strings (``--learning-rate`` 0.0005, ``--max-epochs`` 300,
 ``--hidden-neurons`` 300) -- a user switching over gets the same behaviour for the same command line.  Written as
-a table so the whole surface is visible at a glance; two GPU-only flags (``--math``, ``--gpus``) are appended.
+a table so the whole surface is visible at a glance; one GPU-only flag (``--math``) is appended.
 """
 import argparse
 

@@ -90,15 +90,23 @@ def choose_genes(ranked, metric_values, sub_outputdim, threshold, limit=None):
 
 
 def pad_user_genes(user_genes, ranked, sub_outputdim):
-    """User-supplied gene list padded up to one sub-network (``multinet.py:196-209``; only meaningful < O)."""
+    """User-supplied gene list padded up to a whole number of sub-networks (``multinet.py:196-209``).
+
+    For fewer than ``sub_outputdim`` genes this is the reference's rule: the best-ranked genes fill the sub-network,
+    random ones (with replacement) top it up when the ranking is too short.  For MORE than ``sub_outputdim`` genes
+    that are not a multiple of it the reference's slice ``gene_metric.index[:O - n]`` goes negative and appends almost
+    every gene; here the list is padded to the next multiple of ``sub_outputdim`` by the same rule, so every requested
+    gene is imputed and nothing else changes (deliberate difference)."""
+    user_genes = np.asarray(user_genes)
     n = len(user_genes)
-    if n % sub_outputdim == 0:
-        return np.asarray(user_genes)
-    filler = ranked[:max(sub_outputdim - n, 0)]
-    short = sub_outputdim - n - len(filler)
+    need = (-n) % sub_outputdim
+    if need == 0:
+        return user_genes
+    filler = ranked[:need]
+    short = need - len(filler)
     if short > 0:
         filler = np.concatenate([filler, ranked[np.random.choice(len(ranked), short, replace=True)]])
-    return np.concatenate([np.asarray(user_genes), filler])
+    return np.concatenate([user_genes, filler])
 
 
 def assign_targets(genes, sub_outputdim, mode="random"):
@@ -129,9 +137,11 @@ def abs_correlation(raw_values, rows, cols=None):
     if cols is None:
         c = np.abs(np.corrcoef(raw_values[:, rows].T))
         return np.nan_to_num(c, nan=0.0, posinf=np.inf, neginf=-np.inf)
-    x = np.asarray(raw_values, dtype=np.float64)
-    a = x[:, rows] - x[:, rows].mean(0)
-    b = x[:, cols] - x[:, cols].mean(0)
+    # only the columns involved are widened to float64 (never the whole matrix: 48 GB at 200k x 30k)
+    a = np.asarray(raw_values[:, rows], dtype=np.float64)
+    b = np.asarray(raw_values[:, cols], dtype=np.float64)
+    a -= a.mean(0)
+    b -= b.mean(0)
     with np.errstate(invalid="ignore", divide="ignore"):
         c = (a.T @ b) / np.sqrt(np.outer((a * a).sum(0), (b * b).sum(0)))
     return np.nan_to_num(np.abs(np.clip(c, -1, 1)), nan=0.0)

@@ -111,3 +111,48 @@ def test_c3_sampled_subnetworks_match_oracle():
     """configs[2], the benchmarked configuration: 50k x 20k, S 40, 743 Adam steps per epoch; one epoch, sub-networks
     3 and 38 (first and last sub-network groups of the epoch graph)."""
     _check_sampled("c3", [3, 38], epochs=1)
+
+
+@pytest.mark.parametrize("knobs", [
+    {"DEEPIMPUTE_B200_LT": "0"},                                   # converter-warp kernels (state streams from HBM)
+    {"DEEPIMPUTE_B200_LT": "1", "DEEPIMPUTE_B200_SPLITK": "1"},    # every operand by TMA, one CTA per tile
+    {"DEEPIMPUTE_B200_LT": "1", "DEEPIMPUTE_B200_SPLITK": "2"},    # ... K loop split over 2 / 4 CTAs
+    {"DEEPIMPUTE_B200_LT": "1", "DEEPIMPUTE_B200_SPLITK": "4"},
+], ids=["converter", "lt", "lt-split2", "lt-split4"])
+def test_kernel_families_follow_the_oracle(monkeypatch, knobs):
+    """The engine picks its forward / backward kernel family from the size of the optimiser state (kernels_tc.cu,
+    tc_init).  Every family, forced here on one default-topology problem, follows the oracle through an epoch of 40
+    Adam steps in graph mode, partial last batch included."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(11)
+    n_pred = [540, 513, 600]
+    N, G = 40 * 64 - 17 + 128, 2400
+    lam = rng.gamma(0.6, 3.0, size=(1, G)) * rng.gamma(2.0, 0.5, size=(N, 1))
+    norm = np.log1p(rng.poisson(lam)).astype(np.float32)
+    perm = rng.permutation(G)
+    targ = perm[:3 * O].reshape(3, O).astype(np.int32)
+    pred_idx = [rng.choice(perm[3 * O:], p, replace=False).astype(np.int32) for p in n_pred] if G - 3 * O >= 600 else \
+        [rng.choice(G, p, replace=False).astype(np.int32) for p in n_pred]
+    tr, te = np.arange(N - 128, dtype=np.int32), np.arange(N - 128, N, dtype=np.int32)
+    eng = Engine(n_pred, hidden=H, sub_outputdim=O, learning_rate=1e-3, batch_size=64, dropout_rate=RATE, seed=SEED)
+    want_family = "fwd/bwd=lt splitk={}".format(knobs["DEEPIMPUTE_B200_SPLITK"]) if knobs["DEEPIMPUTE_B200_LT"] == "1" else "fwd/bwd=ts"
+    assert want_family in eng.describe(), eng.describe()
+    eng.set_data(norm, pred_idx, targ)
+    eng.set_split(tr, te)
+    ref = OracleNet(n_pred, H, O, learning_rate=1e-3, batch_size=64, dropout_rate=RATE, seed=SEED)
+    Xtr, Ytr = stage(norm, pred_idx, targ, tr)
+    Xte, Yte = stage(norm, pred_idx, targ, te)
+    step = 0
+    for epoch in range(2):
+        p = epoch_permutation(SEED, epoch, len(tr))
+        got = eng.train_epoch(p)
+        loss, step = ref.train_epoch(Xtr, Ytr, p, step)
+        np.testing.assert_allclose(got, (loss, ref.loss(Xte, Yte)), rtol=1e-3)
+    assert eng.graph_fallbacks() == 0
+    want = np.hstack(ref.forward(stage(norm, pred_idx, targ, np.arange(N))[0]))
+    assert rel_err(eng.predict(), want) < 2e-3
+    for got_w, ref_w in zip(eng.get_weights(), ref.get_weights()):
+        for a, b in zip(got_w, ref_w):
+            assert rel_err(a, b) < 2e-3
+    eng.close()

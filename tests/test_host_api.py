@@ -142,3 +142,20 @@ def test_deepimpute_entry_point_runs_on_csv(tmp_path, monkeypatch):
     out2 = entry.deepImpute(inputFile=str(path), output=str(tmp_path / "o.csv"), max_epochs=1, hidden_neurons=8,
                             output_neurons=16, limit="20", cores=1, cell_axis="columns")
     assert out2 is None and (tmp_path / "o.csv").exists()
+
+
+def test_unknown_genes_to_impute_raise_like_the_reference():
+    # the reference raises KeyError (reindex / .loc, multinet.py:213, :356); get_indexer's -1 must not become "last column"
+    raw = synthetic_counts(60, 40, seed=2)
+    net = CpuMultiNet(ncores=1, sub_outputdim=8, max_epochs=1, verbose=0,
+                      architecture=[{"type": "dense", "neurons": 4, "activation": "relu"}])
+    with pytest.raises(KeyError, match="NOPE"):
+        net.fit(raw, genes_to_impute=["g1", "g2", "NOPE"], minVMR=0.0)
+
+
+def test_sharded_fit_needs_a_seed():
+    from deepimpute_b200.parallel import ShardContext
+    raw = synthetic_counts(60, 40, seed=2)
+    net = CpuMultiNet(ncores=1, sub_outputdim=8, max_epochs=1, verbose=0, seed=None, shard=ShardContext(0, 2))
+    with pytest.raises(ValueError, match="seed"):
+        net.fit(raw)

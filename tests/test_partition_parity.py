@@ -176,3 +176,65 @@ def test_statistics_based_filters_equal_the_pandas_ones(test_counts):
     m0, v0 = raw0.mean().values, raw0.var().values
     assert 5 not in partition.candidate_predictors_from_stats(m0, v0) and 5 not in partition.rank_genes_from_stats(m0, v0)[0]
     np.testing.assert_array_equal(partition.candidate_predictors(raw0), partition.candidate_predictors_from_stats(m0, v0))
+
+
+# ---- n_pred: candidate predictors capped at the n_pred genes with the largest std/mean (multinet.py:25-33) -----------
+def _reference_partition_n_pred(ref, raw, seed, sub_outputdim, NN_lim, ntop, n_pred):
+    net = ref.MultiNet.__new__(ref.MultiNet)
+    net.sub_outputdim, net.seed = sub_outputdim, seed
+    np.random.seed(seed)
+    gene_metric = (raw.var() / (1 + raw.mean())).sort_values(ascending=False)
+    gene_metric = gene_metric[gene_metric > 0]
+    genes = net.filter_genes(gene_metric, 0.5, NN_lim=NN_lim)
+    cov = ref.get_distance_matrix(raw, n_pred=n_pred)
+    net.setTargets(raw.reindex(columns=genes), mode="random")
+    net.setPredictors(cov, ntop=ntop)                # KeyError when a target is not among the n_pred candidates
+    cols = raw.columns
+    return dict(targets=cols.get_indexer(net.targets.reshape(-1)).reshape(net.targets.shape),
+                predictors=[cols.get_indexer(p) for p in net.predictors])
+
+
+def test_live_reference_n_pred_where_the_reference_does_not_raise():
+    """With every target inside the candidate set the reference's n_pred path works (multinet.py:356-358) and this
+    port must pick the same predictors.  n_pred = number of genes with std/mean > 0 keeps every gene a candidate but
+    takes the n_pred branch (candidates in std/mean order instead of column order)."""
+    ref = _import_reference()
+    raw = synthetic_counts(150, 80, seed=9)
+    cv = raw.std() / raw.mean()
+    n_pred = int((cv > 0).sum())
+    want = _reference_partition_n_pred(ref, raw, 3, 16, None, 5, n_pred)
+    got = host_partition(raw, 3, sub_outputdim=16, n_pred=n_pred)
+    np.testing.assert_array_equal(got["targets"], want["targets"])
+    for a, b in zip(got["predictors"], want["predictors"]):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_n_pred_semantic_where_the_reference_raises():
+    """Targets outside the n_pred candidates make the reference raise KeyError (cov.loc[targets] has no such rows,
+    SURVEY.md 7.2).  Defined semantic here (DESIGN.md section 9): rows = ALL targets, columns = the n_pred candidates;
+    checked against a brute-force float64 restatement.  The whole matrix is never widened to float64."""
+    raw = synthetic_counts(200, 120, seed=4).astype(np.float32)
+    n_pred = 30
+    got = host_partition(raw, 5, sub_outputdim=16, n_pred=n_pred)
+    cand = partition.candidate_predictors(raw, n_pred)
+    assert len(cand) == n_pred
+    x = raw.values.astype(np.float64)
+    c = np.abs(np.corrcoef(x.T))
+    labels = np.asarray(raw.columns, dtype=object)
+    for t, p in zip(got["targets"], got["predictors"]):
+        assert not np.isin(t, cand).all()                              # the case the reference cannot handle
+        keep = np.array(sorted(np.setdiff1d(cand, t), key=lambda g: labels[g]))
+        top = np.argsort(-c[np.ix_(t, keep)], axis=1)[:, :5].ravel()
+        np.testing.assert_array_equal(p, pd.unique(keep[top]))
+        assert np.isin(p, cand).all() and len(p) <= n_pred
+
+
+def test_user_gene_list_longer_than_one_subnetwork_is_padded_to_a_multiple():
+    raw = synthetic_counts(60, 64, seed=1)
+    ranked, _ = partition.rank_genes(raw)
+    np.random.seed(0)
+    user = np.arange(20)
+    genes = partition.pad_user_genes(user, ranked, 16)
+    assert len(genes) == 32 and list(genes[:20]) == list(user)         # every requested gene is kept
+    assert len(partition.pad_user_genes(np.arange(10), ranked, 16)) == 16
+    assert len(partition.pad_user_genes(np.arange(32), ranked, 16)) == 32
