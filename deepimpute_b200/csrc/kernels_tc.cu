@@ -678,6 +678,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
     if (warp != LT_EPI_WARPS) pdl_wait();                 // the producer waits later: see below
+    // few sub-networks per GPU: SMs are idle, so the dependent grid may as well take its seats now, run its prologue
+    // and fetch its weights while this grid works (it still waits for this grid's completion before touching its output)
+    if (p.pdl_early && threadIdx.x == 0) pdl_release();
     DI_TRACE_T0(1);
 
     if (warp == LT_EPI_WARPS) {
@@ -805,14 +808,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
 #pragma unroll
                 for (int i = 0; i < 16; ++i) mine[(int64_t)(c + i) * TILE_M] = nkb > 0 ? v[i] : 0.f;
             }
-            __threadfence();
+            // the CTA barrier orders every thread's stores before thread 0's release at GPU scope (cumulativity), and
+            // thread 0's acquire before every thread's loads after the second barrier: one atomic instead of 512 fences
             named_bar_sync(1, LT_EPI_WARPS * 32);
             if (threadIdx.x == 0) {
                 unsigned int* cnt = p.kcount + (int64_t)s * p.m_tiles + m_tile;
-                const unsigned int prev = atomicAdd(cnt, 1u);
+                unsigned int prev;
+                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(cnt) : "memory");
                 if (prev == (unsigned int)(ks - 1)) *cnt = 0u;     // everybody has arrived: ready for the next launch
                 arrival_slot = prev;
-                __threadfence();
             }
             named_bar_sync(1, LT_EPI_WARPS * 32);
             if (arrival_slot == (unsigned int)(ks - 1)) ksum = p.kpart + tile * (int64_t)ncol * TILE_M + fl;
@@ -1474,6 +1478,7 @@ struct TcState {
     bool adam_big = false;                                 // one-CTA-per-SM ADAM kernel (DEEPIMPUTE_B200_ADAM=ring disables it)
     bool pdl = true;                                       // programmatic dependent launch along a step's kernel chain (DEEPIMPUTE_B200_PDL=0 disables)
     bool pdl_early = false;                                // DEEPIMPUTE_B200_PDL=2: dependents released before the main loop instead of after it
+    bool pdl_early_adam = false;                           // ... the ADAM kernel too (its successor is the next step's FWD1)
     bool pdl_prefetch = true;                              // DEEPIMPUTE_B200_PDL_PREFETCH=0: wait for the previous grid before any load
     int pdl_lead = 0;                                      // DEEPIMPUTE_B200_PDL_LEAD=k: release dependents k K blocks before the main loop ends
     int smem_adam_big = 0, ad_nded = 0, ad_stride = 0, ad_groups = 4, ad_kg = 2;
@@ -1620,7 +1625,7 @@ bool tc_init(Engine& e) {
     st->x3_bwd = st->x3;
     if (const char* v = getenv("DEEPIMPUTE_B200_EXPERIMENT")) st->simt_adam = atoi(v) & 2;
     if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_STORE")) st->adam_direct = strcmp(v, "tma") != 0;
-    if (const char* v = getenv("DEEPIMPUTE_B200_PDL")) { st->pdl = atoi(v) != 0; st->pdl_early = atoi(v) == 2; }
+    if (const char* v = getenv("DEEPIMPUTE_B200_PDL")) { st->pdl = atoi(v) != 0; st->pdl_early = st->pdl_early_adam = atoi(v) == 2; }
     if (const char* v = getenv("DEEPIMPUTE_B200_PDL_PREFETCH")) st->pdl_prefetch = atoi(v) != 0;
     if (const char* v = getenv("DEEPIMPUTE_B200_PDL_LEAD")) st->pdl_lead = std::max(0, atoi(v));
     for (int deep = 0; deep < 2; ++deep) {
@@ -1691,6 +1696,17 @@ bool tc_init(Engine& e) {
             for (int s = 0; s < e.S; ++s) min_kb = std::min(min_kb, e.Pp[s] / BLOCK_K);
             st->lt_ks = std::max(1, std::min(std::min(4, min_kb), 148 / std::max(1, mh * e.S)));
             if (const char* v = getenv("DEEPIMPUTE_B200_SPLITK")) st->lt_ks = std::max(1, std::min(std::min(8, min_kb), atoi(v)));
+            // dependents released at once (not after the accumulator) when the CTAs of two consecutive kernels of
+            // every group fit on the machine together: waiting CTAs then cost nothing (measured at 40 sub-networks
+            // per GPU, where they do not fit, early release is a loss: DESIGN.md 3.6)
+            const int mo = (e.Op + TILE_M - 1) / TILE_M;
+            const int widest = std::max(st->lt_ks * mh + mo, mo + st->lt_ks * mh) * e.S;   // FWD1+FWD2 or FWD2+BWD alive together
+            int adam_ctas = 0;
+            for (int s = 0; s < e.S; ++s) adam_ctas += ((e.Pp[s] + ADAM_TILE - 1) / ADAM_TILE) * mh + ((e.Hp + ADAM_TILE - 1) / ADAM_TILE) * mo;
+            if (!getenv("DEEPIMPUTE_B200_PDL")) {
+                st->pdl_early = widest <= 148;
+                st->pdl_early_adam = st->pdl_early && adam_ctas + st->lt_ks * mh * e.S <= 148;
+            }
             if (st->lt_ks > 1) {
                 const size_t tiles = (size_t)e.S * mh;
                 for (int k = 0; k < 2 && ok; ++k) {
@@ -1950,6 +1966,7 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     q.row0 = a.row0; q.wbox = st->wbox1; q.wbox2 = st->wbox2;
     q.W1 = e.W1; q.mW1 = e.mW1; q.vW1 = e.vW1; q.W2 = e.W2; q.mW2 = e.mW2; q.vW2 = e.vW2;
     q.W1lo = st->lt ? e.W1lo : nullptr; q.W2lo = st->lt ? e.W2lo : nullptr;
+    q.pdl_early = (st->pdl_early_adam && pl.graph) ? 1 : 0;
     q.adam_direct = st->adam_direct ? 1 : 0;
     if (!pl.graph && st->d_trace) q.trace = st->d_trace + 768;
     int maxPp = 0;
@@ -2105,10 +2122,11 @@ const char* tc_describe(Engine& e) {
     auto* st = static_cast<TcState*>(e.tc);
     if (!st) return "fp32 CUDA-core kernels";
     snprintf(buf, sizeof buf,
-             "fwd/bwd=%s splitk=%d stages=%d/%d adam=%s groups=%d graph=%d pdl=%d l2_window=%d (%.1f MB of %.1f MB state, hitRatio %.2f) graph_fallbacks=%lld",
+             "fwd/bwd=%s splitk=%d stages=%d/%d adam=%s groups=%d graph=%d pdl=%d%s l2_window=%d (%.1f MB of %.1f MB state, hitRatio %.2f) graph_fallbacks=%lld",
              st->lt ? "lt" : (st->ts ? "ts" : (st->x3 ? "x3-smem" : "tf32")), st->lt ? st->lt_ks : 1,
              st->lt ? st->lt_train.stages : st->fwd1_train[1].stages, st->lt ? st->lt_infer.stages : st->infer.stages,
-             st->adam_big ? "resident" : "ring", st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0, st->l2_window ? 1 : 0,
+             st->adam_big ? "resident" : "ring", st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0,
+             st->pdl_early_adam ? "(early release, all four kernels)" : (st->pdl_early ? "(early release, fwd/bwd)" : ""), st->l2_window ? 1 : 0,
              st->l2_window ? st->l2_policy.num_bytes * (double)st->l2_policy.hitRatio / 1048576.0 : 0.0,
              e.state_bytes / 1048576.0, st->l2_window ? (double)st->l2_policy.hitRatio : 0.0, (long long)st->graph_fallbacks);
     return buf;

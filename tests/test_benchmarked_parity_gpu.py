@@ -43,7 +43,7 @@ def _workload(name):
     return wl, norm
 
 
-def _check_sampled(name, sampled, epochs):
+def _check_sampled(monkeypatch, name, sampled, epochs):
     wl, norm = _workload(name)
     B = wl["B"]
     n_pred = [len(p) for p in wl["pred_idx"]]
@@ -62,9 +62,14 @@ def _check_sampled(name, sampled, epochs):
     rows = np.random.default_rng(5).choice(wl["N"], 1500, replace=False).astype(np.int32)
     full_pred = full.predict(rows=rows)
     full_w = full.get_weights()
+    family = full.describe()
     full.close()
 
-    # (4) the sampled sub-networks alone on the device: same trajectory, bit for bit
+    # (4) the sampled sub-networks alone on the device: same trajectory, bit for bit.  The engine picks its kernel
+    # family from the size of the optimiser state (and the split-K factor from the number of sub-networks): the small
+    # engine is pinned to the family the full model ran with, since families differ in summation order
+    monkeypatch.setenv("DEEPIMPUTE_B200_LT", "1" if "fwd/bwd=lt" in family else "0")
+    monkeypatch.setenv("DEEPIMPUTE_B200_SPLITK", family.split("splitk=")[1].split()[0])
     sel_pred = [wl["pred_idx"][s] for s in sampled]
     sel_targ = np.ascontiguousarray(wl["targ_idx"][sampled])
     sel_np = [n_pred[s] for s in sampled]
@@ -101,16 +106,16 @@ def _check_sampled(name, sampled, epochs):
     return fh
 
 
-def test_c2_sampled_subnetworks_match_oracle():
+def test_c2_sampled_subnetworks_match_oracle(monkeypatch):
     """configs[1]: 10k x 5k, S 10, 149 Adam steps per epoch; two epochs, sub-networks 0, 4 and 9."""
-    fh = _check_sampled("c2", [0, 4, 9], epochs=2)
+    fh = _check_sampled(monkeypatch, "c2", [0, 4, 9], epochs=2)
     assert fh[1, 0] < fh[0, 0]
 
 
-def test_c3_sampled_subnetworks_match_oracle():
+def test_c3_sampled_subnetworks_match_oracle(monkeypatch):
     """configs[2], the benchmarked configuration: 50k x 20k, S 40, 743 Adam steps per epoch; one epoch, sub-networks
     3 and 38 (first and last sub-network groups of the epoch graph)."""
-    _check_sampled("c3", [3, 38], epochs=1)
+    _check_sampled(monkeypatch, "c3", [3, 38], epochs=1)
 
 
 @pytest.mark.parametrize("knobs", [
