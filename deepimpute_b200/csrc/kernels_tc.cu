@@ -1425,6 +1425,210 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
     DI_TRACE_T0(5);
 }
 
+// --------------------------------------------------------------------------- ADAM, one CTA per SM, 128-bit epilogue
+// Same tile, operands and arithmetic as tc_adam_big_kernel with the two MMA operands SWAPPED: A = `in`, B = `dout`
+// (both are [32 k][128] MN-major tiles of one layout, so the swap is free), which puts the tile's INPUT rows on the 128
+// TMEM lanes and its OUTPUT features -- the contiguous dimension of W[in][out] -- on the accumulator columns.  A thread
+// then owns one weight row and consecutive features: w, m, v arrive as 128-bit shared loads and leave (with W_lo) as
+// 128-bit global stores.  The epilogue of tc_adam_big_kernel issues 56 32-bit memory instructions per 8 weights and is
+// bound by the issue rate of the load/store unit (about 1000 warp instructions per 2000 cycles, traces r02b); here it
+// is 14 per 8 weights.
+//   chunk g (0..3) = features [32 g, 32 g + 32) x 128 rows x {w, m, v}: 3 x 16 KB, delivered by TMA as 32-row boxes with
+//   the 128-byte swizzle (a thread reads its own 128-byte row: chunk j of row r sits at j ^ (r & 7), so the 128-bit
+//   loads of a quarter warp hit eight different bank groups); the first `ad_nded` chunks have dedicated stages filled
+//   while the MMAs run, the others land in the operand area once the accumulator is complete.
+//   warp (q, g): TMEM lane quadrant q = rows 32 q .., feature chunk g; 16 epilogue warps + TMA warp + MMA warp.
+struct AdamVecMaps { CUtensorMap A, B, Alo, Blo, W, M, V; };   // dout, in, twins; w / m / v as [32 rows][32 features] swizzled boxes
+constexpr int ADV_CHUNK_BYTES = 3 * TILE_M * 32 * 4;      // 48 KB
+
+template <bool X3>
+__global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_vec_kernel(const __grid_constant__ AdamVecMaps maps1,
+                                                                       const __grid_constant__ AdamVecMaps maps2, const TcParams p) {
+    const int s = blockIdx.z + p.s_base;
+    const SubnetDesc d = p.desc[s];
+    const bool second = (int)blockIdx.x >= p.nx1;
+    const AdamVecMaps* mp = second ? &maps2 : &maps1;
+    const CUtensorMap &mapA = mp->A, &mapB = mp->B, &mapAlo = mp->Alo, &mapBlo = mp->Blo, &mapW = mp->W, &mapM = mp->M, &mapV = mp->V;
+    const int m0 = blockIdx.y * TILE_M;                    // first output feature of the tile
+    const int n0 = ((int)blockIdx.x - (second ? p.nx1 : 0)) * ADAM_TILE;   // first input row of the tile
+    int out_dim, in_dim, a_c0, b_c0, b_c1;
+    int64_t row_base;
+    if (!second) { out_dim = p.Hp; in_dim = d.Pp; a_c0 = s * p.Hp + m0; b_c0 = (int)d.coff + n0; b_c1 = (int)p.row0; row_base = d.coff; }
+    else { out_dim = p.Op; in_dim = p.Hp; a_c0 = s * p.Op + m0; b_c0 = s * p.Hp + n0; b_c1 = 0; row_base = (int64_t)s * p.Hp; }
+    if (m0 >= out_dim || n0 >= in_dim) return;
+    const int nkb = p.nkb_adam;
+    const int rows_ok = min(ADAM_TILE, in_dim - n0);       // multiple of 32
+    const int nrb = rows_ok / 32;                          // 32-row boxes per chunk and tensor
+    const int nfc = min(4, (out_dim - m0) / 32);           // 32-feature chunks of this tile (out_dim is a multiple of 32)
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int NSETS = X3 ? 4 : 2;
+    const uint32_t set_bytes = (uint32_t)nkb * A_STAGE_BYTES;
+    uint8_t* set0 = smem;                                           // dout_hi
+    uint8_t* set1 = smem + set_bytes;                               // in_lo   (plain TF32: in)
+    uint8_t* set2 = smem + 2 * (size_t)set_bytes;                   // in_hi
+    uint8_t* set3 = smem + 3 * (size_t)set_bytes;                   // dout_lo
+    uint8_t* ded = smem + (size_t)NSETS * set_bytes;
+    auto stage_ptr = [&](int g) -> uint8_t* {
+        return g < p.ad_nded ? ded + (size_t)g * ADV_CHUNK_BYTES : smem + (size_t)(g - p.ad_nded) * ADV_CHUNK_BYTES;
+    };
+    __shared__ uint64_t ops_bar[2], tmem_full_bar, wfull[4];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int TMA_WARP = 4 * AD_MAX_GROUPS, MMA_WARP = TMA_WARP + 1;
+    DI_TRACE_T0(0);
+    if (threadIdx.x == 0) {
+        mbar_init(&ops_bar[0], 1); mbar_init(&ops_bar[1], 1); mbar_init(&tmem_full_bar, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&wfull[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    if (warp != TMA_WARP) pdl_wait();
+    if (p.pdl_early && threadIdx.x == 0) pdl_release();
+    __syncwarp();
+
+    if (warp == TMA_WARP) {
+        if (elect_one()) {
+            auto load_set = [&](const CUtensorMap* m, uint8_t* dst, uint64_t* bar, int c0, int c1) {
+                for (int kb = 0; kb < nkb; ++kb)
+                    load_stage<true>(dst + (size_t)kb * A_STAGE_BYTES, m, bar, c0, c1 + kb * BLOCK_K, TILE_M);
+            };
+            auto load_chunk = [&](int g) {
+                uint8_t* st = stage_ptr(g);
+                mbar_arrive_expect_tx(&wfull[g], 3u * (uint32_t)nrb * 4096u);
+                const int32_t c0 = m0 + 32 * g;
+                for (int rb = 0; rb < nrb; ++rb) {
+                    const int32_t r = (int32_t)(row_base + n0 + 32 * rb);
+                    tma_load_2d(st + rb * 4096, &mapW, &wfull[g], c0, r);
+                    tma_load_2d(st + 16384 + rb * 4096, &mapM, &wfull[g], c0, r);
+                    tma_load_2d(st + 32768 + rb * 4096, &mapV, &wfull[g], c0, r);
+                }
+            };
+            // ADAM follows BWD, which writes dz1 (the `dout` of the W1 tiles) and nothing else this kernel reads
+            const bool a_free = p.pdl_prefetch && second;
+            const bool early = p.pdl_prefetch != 0;
+            if constexpr (X3) {
+                mbar_arrive_expect_tx(&ops_bar[0], 3u * set_bytes);
+                mbar_arrive_expect_tx(&ops_bar[1], set_bytes);
+            } else {
+                mbar_arrive_expect_tx(&ops_bar[0], 2u * set_bytes);
+            }
+            auto load_in = [&]() {
+                if constexpr (X3) { load_set(&mapBlo, set1, &ops_bar[0], b_c0, b_c1); load_set(&mapB, set2, &ops_bar[0], b_c0, b_c1); }
+                else load_set(&mapB, set1, &ops_bar[0], b_c0, b_c1);
+            };
+            auto load_dout = [&]() {
+                load_set(&mapA, set0, &ops_bar[0], a_c0, 0);
+                if constexpr (X3) load_set(&mapAlo, set3, &ops_bar[1], a_c0, 0);
+            };
+            if (early) {
+                load_in();
+                if (a_free) load_dout();
+                for (int g = 0; g < min(p.ad_nded, nfc); ++g) load_chunk(g);
+                pdl_wait();
+                if (!a_free) load_dout();
+            } else {
+                pdl_wait();
+                load_dout(); load_in();
+                for (int g = 0; g < min(p.ad_nded, nfc); ++g) load_chunk(g);
+            }
+            if (nfc > p.ad_nded) {                                 // the operand area becomes chunk stages
+                mbar_wait(&tmem_full_bar, 0, 4);
+                for (int g = p.ad_nded; g < nfc; ++g) load_chunk(g);
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        if (elect_one()) {
+            const uint32_t idesc = idesc_for(TILE_M, true, true);      // M = 128 input rows, N = 128 output features
+            auto mma_round = [&](const uint8_t* in_t, const uint8_t* dout_t, bool first) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint32_t sa = smem_u32(in_t + (size_t)kb * A_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(dout_t + (size_t)kb * A_STAGE_BYTES);
+#pragma unroll
+                    for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
+                        umma_tf32(tmem, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (!first || kb || j) ? 1u : 0u);
+                }
+            };
+            mbar_wait(&ops_bar[0], 0, 6);
+            tc_fence_after();
+            mma_round(set1, set0, true);                               // in_lo dout_hi   (plain TF32: in dout)
+            if constexpr (X3) {
+                mma_round(set2, set0, false);                          // in_hi dout_hi
+                mbar_wait(&ops_bar[1], 0, 6);
+                tc_fence_after();
+                mma_round(set2, set3, false);                          // in_hi dout_lo
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        const int quad = warp & 3, g = warp >> 2;          // TMEM lane quadrant (rows 32 quad ..), feature chunk
+        const int r = quad * 32 + lane;                    // input row inside the tile
+        const bool row_ok = r < rows_ok;
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * g);
+        const AdamParams adam = adam_of(p);
+        DI_TRACE_T0(2);
+        mbar_wait(&tmem_full_bar, 0, 4);
+        tc_fence_after();
+        if (threadIdx.x == 0 && !p.pdl_early) pdl_release();
+        __syncwarp();
+        DI_TRACE_T0(3);
+        if (g < nfc) {
+            mbar_wait(&wfull[g], 0, 7);
+            if (p.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[8] = clock64();
+            __syncwarp();
+            // this thread's 128-byte row of the chunk: box rb = r / 32, row r % 32, 16-byte piece j at j ^ (r & 7)
+            const uint32_t rowb = smem_u32(stage_ptr(g)) + (uint32_t)(r >> 5) * 4096u + (uint32_t)(r & 31) * 128u;
+            const uint32_t sw = (uint32_t)(r & 7);
+            const int64_t off = (row_base + n0 + r) * (int64_t)out_dim + m0 + 32 * g;
+            float* gw = (second ? p.W2 : p.W1) + off;
+            float* gm = (second ? p.mW2 : p.mW1) + off;
+            float* gv = (second ? p.vW2 : p.vW1) + off;
+            float* gl0 = second ? p.W2lo : p.W1lo;
+            float* gl = gl0 ? gl0 + off : nullptr;
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) {            // 8 features per pass
+                float acc[8];
+                __syncwarp();
+                tmem_ld8(taddr + 8 * sub, acc);
+                if (!row_ok) continue;
+                float w[8], m[8], v[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t a = rowb + (((uint32_t)(2 * sub + h) ^ sw) << 4);
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w[4 * h]), "=f"(w[4 * h + 1]), "=f"(w[4 * h + 2]), "=f"(w[4 * h + 3]) : "r"(a));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(m[4 * h]), "=f"(m[4 * h + 1]), "=f"(m[4 * h + 2]), "=f"(m[4 * h + 3]) : "r"(a + 16384u));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * h]), "=f"(v[4 * h + 1]), "=f"(v[4 * h + 2]), "=f"(v[4 * h + 3]) : "r"(a + 32768u));
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) adam_update_fast(acc[i], w[i], m[i], v[i], adam);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int o = 8 * sub + 4 * h;
+                    *reinterpret_cast<float4*>(gw + o) = make_float4(w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]);
+                    *reinterpret_cast<float4*>(gm + o) = make_float4(m[4 * h], m[4 * h + 1], m[4 * h + 2], m[4 * h + 3]);
+                    *reinterpret_cast<float4*>(gv + o) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+                    if (gl) *reinterpret_cast<float4*>(gl + o) = make_float4(tf32_residual(w[4 * h]), tf32_residual(w[4 * h + 1]),
+                                                                          tf32_residual(w[4 * h + 2]), tf32_residual(w[4 * h + 3]));
+                }
+            }
+            if (p.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[48] = clock64();
+        }
+        __syncwarp();
+        DI_TRACE_T0(4);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+    DI_TRACE_T0(5);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct TcState {
     // weights / step buffers (fixed for the life of the engine)
@@ -1439,6 +1643,9 @@ struct TcState {
     CUtensorMap Xstep_k, Xstep_mn, Ystep_aux;
     CUtensorMap Xchunk_k, Hchunk_k;                        // inference chunk
     CUtensorMap W1_t[3], W2_t[3];                          // {w, m, v} tiles of the ADAM epilogue
+    CUtensorMap W1_v[3], W2_v[3];                          // ... as [32 rows][32 features] swizzled boxes (tc_adam_vec_kernel)
+    bool adam_vec = false;                                 // 128-bit ADAM epilogue (DEEPIMPUTE_B200_ADAM_VEC=0: the 32-bit one)
+    int adv_nded = 0, smem_adam_vec = 0;
     // LT kernels (every operand by TMA): residual twins of the weights and K-major views of the activation twins
     bool lt = false;                                       // DEEPIMPUTE_B200_LT=0 selects the converter-warp kernels
     CUtensorMap W1lo_mn, W2lo_mn, W2lo_k, Hlo_k, DZ2lo_k, Xstep_lo_k, Xtr_lo_k, Xte_lo_k, Xchunk_lo_k, Hchunk_lo_k;
@@ -1616,6 +1823,8 @@ bool tc_init(Engine& e) {
     for (int i = 0; i < 3; ++i) {
         ok = ok && make_map_plain(&st->W1_t[i], w1[i], e.PT, e.Hp, e.Hp, st->wbox1, AD_R);
         ok = ok && make_map_plain(&st->W2_t[i], w2[i], SH, e.Op, e.Op, st->wbox2, AD_R);
+        ok = ok && make_map_2d(&st->W1_v[i], w1[i], e.PT, e.Hp, e.Hp, 32);
+        ok = ok && make_map_2d(&st->W2_v[i], w2[i], SH, e.Op, e.Op, 32);
     }
     if (!ok) { e.err = "cuTensorMapEncodeTiled failed"; return false; }
     // shared-memory budgets.  The side-operand tile (aux) is dropped for the compensated FWD2, whose doubled slabs
@@ -1777,6 +1986,11 @@ bool tc_init(Engine& e) {
         st->adam_big = st->ad_nded >= 1 && (AD_MAX_CHUNKS - st->ad_nded) * st->ad_stride <= ops;
         st->smem_adam_big = ops + st->ad_nded * st->ad_stride + 1024;
         if (const char* v = getenv("DEEPIMPUTE_B200_ADAM")) if (!strcmp(v, "ring")) st->adam_big = false;
+        // 128-bit epilogue: 4 chunks of 48 KB, `adv_nded` of them in dedicated stages, the rest in the operand area
+        st->adv_nded = room > 0 ? std::min(4, room / ADV_CHUNK_BYTES) : 0;
+        st->adam_vec = st->adam_big && (4 - st->adv_nded) * ADV_CHUNK_BYTES <= ops;
+        st->smem_adam_vec = ops + st->adv_nded * ADV_CHUNK_BYTES + 1024;
+        if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_VEC")) st->adam_vec = st->adam_vec && atoi(v) != 0;
         if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_GROUPS")) st->ad_groups = std::max(1, std::min(AD_MAX_GROUPS, atoi(v)));
     }
     if (st->smem_adam > 227 * 1024 || !st->fwd1_train[0].stages || !st->fwd2_train[0].stages || !st->bwd_train[0].stages ||
@@ -1811,6 +2025,10 @@ bool tc_init(Engine& e) {
     if (st->adam_big) {
         set((const void*)tc_adam_big_kernel<false>, st->smem_adam_big);
         set((const void*)tc_adam_big_kernel<true>, st->smem_adam_big);
+    }
+    if (st->adam_vec) {
+        set((const void*)tc_adam_vec_kernel<false>, st->smem_adam_vec);
+        set((const void*)tc_adam_vec_kernel<true>, st->smem_adam_vec);
     }
     if (ce != cudaSuccess) { e.err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return false; }
     return true;
@@ -1983,7 +2201,15 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam");
     q.ad_nded = st->ad_nded; q.ad_stride = st->ad_stride; q.ad_kg = st->ad_kg;
     { static const bool generic = [] { const char* v = getenv("DEEPIMPUTE_B200_ADAM_GENERIC"); return v && atoi(v) != 0; }(); q.ad_generic = generic ? 1 : 0; }
-    if (st->adam_big) {
+    if (st->adam_vec) {
+        AdamVecMaps v1, v2;
+        v1.A = m1.A; v1.B = m1.B; v1.Alo = m1.Alo; v1.Blo = m1.Blo; v1.W = st->W1_v[0]; v1.M = st->W1_v[1]; v1.V = st->W1_v[2];
+        v2.A = m2.A; v2.B = m2.B; v2.Alo = m2.Alo; v2.Blo = m2.Blo; v2.W = st->W2_v[0]; v2.M = st->W2_v[1]; v2.V = st->W2_v[2];
+        q.ad_nded = st->adv_nded;
+        const bool pdl = st->pdl && pl.graph;
+        if (st->x3) launch_k(tc_adam_vec_kernel<true>, grid, NTHREADS_BIG, st->smem_adam_vec, pl.main, pdl, v1, v2, q);
+        else launch_k(tc_adam_vec_kernel<false>, grid, NTHREADS_BIG, st->smem_adam_vec, pl.main, pdl, v1, v2, q);
+    } else if (st->adam_big) {
         const int nthreads = (4 * st->ad_groups + 2) * 32;
         const bool pdl = st->pdl && pl.graph;
         if (st->x3) launch_k(tc_adam_big_kernel<true>, grid, nthreads, st->smem_adam_big, pl.main, pdl, m1, m2, q);
@@ -2125,7 +2351,7 @@ const char* tc_describe(Engine& e) {
              "fwd/bwd=%s splitk=%d stages=%d/%d adam=%s groups=%d graph=%d pdl=%d%s l2_window=%d (%.1f MB of %.1f MB state, hitRatio %.2f) graph_fallbacks=%lld",
              st->lt ? "lt" : (st->ts ? "ts" : (st->x3 ? "x3-smem" : "tf32")), st->lt ? st->lt_ks : 1,
              st->lt ? st->lt_train.stages : st->fwd1_train[1].stages, st->lt ? st->lt_infer.stages : st->infer.stages,
-             st->adam_big ? "resident" : "ring", st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0,
+             st->adam_vec ? "resident-128bit" : (st->adam_big ? "resident" : "ring"), st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0,
              st->pdl_early_adam ? "(early release, all four kernels)" : (st->pdl_early ? "(early release, fwd/bwd)" : ""), st->l2_window ? 1 : 0,
              st->l2_window ? st->l2_policy.num_bytes * (double)st->l2_policy.hitRatio / 1048576.0 : 0.0,
              e.state_bytes / 1048576.0, st->l2_window ? (double)st->l2_policy.hitRatio : 0.0, (long long)st->graph_fallbacks);
