@@ -407,6 +407,40 @@ def sharding_check(ctx, rank, world, local):
             "ok": bool(diff == 0.0 and loss_rel < 1e-5)}
 
 
+# ------------------------------------------------------------------------------------------- API level
+def api_run(wl, epochs, local):
+    """``MultiNet(...).fit(df, NN_lim=G)`` + ``.predict(df)`` on the workload's raw counts as a float32 DataFrame -- the
+    call a user of the reference makes (multinet.py:169, :266), everything included: input checks, gene statistics,
+    correlation + predictor selection, upload, the epochs, model file, held-out metrics, predict with the fused tail
+    and the float64 DataFrame that comes back.  Twice: ``epochs`` fixed epochs (patience off), and the reference's
+    defaults (max_epochs 500, patience 5: early-stopped)."""
+    import contextlib
+    import pandas as pd
+    from deepimpute_b200 import MultiNet
+    N, G = wl["N"], wl["G"]
+    frame = pd.DataFrame(wl["raw"].numpy(), index=["c{:06d}".format(i) for i in range(N)],
+                         columns=["g{:06d}".format(j) for j in range(G)], copy=False)
+    out = {}
+    for name, kw in (("fixed_epochs", dict(max_epochs=epochs, patience=10 ** 6)), ("early_stopped", dict(max_epochs=500, patience=5))):
+        net = MultiNet(seed=MODEL_SEED, ncores=1, verbose=0, device=local, **kw)
+        with contextlib.redirect_stdout(sys.stderr):
+            t0 = time.perf_counter()
+            net.fit(frame, NN_lim=G)
+            t1 = time.perf_counter()
+            imputed = net.predict(frame)
+            t2 = time.perf_counter()
+        assert imputed.shape == (N, G)
+        out[name] = {"fit_s": round(t1 - t0, 3), "predict_s": round(t2 - t1, 3), "epochs": int(net.trained_epochs),
+                     "value": N * G / (t2 - t0), "unit": "cells*genes/s",
+                     "sub_networks": int(len(net.predictors)),
+                     "test_metrics": {k: float(v) for k, v in net.test_metrics.items()},
+                     "phases": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in net.timings.items()}}
+        if net.engine is not None:
+            net.engine.close()
+        del net, imputed
+    return out
+
+
 # --------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -418,6 +452,9 @@ def main():
     ap.add_argument("--epochs", type=int, default=20, help="training epochs per step (fixed; no early stopping)")
     ap.add_argument("--math", default=None, choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--api", action="store_true",
+                    help="also time the reference-facing API end to end: MultiNet(...).fit(DataFrame, NN_lim=G) + "
+                         ".predict(DataFrame) on the workload's count matrix, fixed epochs and early-stopped (N = 1 only)")
     ap.add_argument("--ref-subnets", type=int, default=4, help="sub-networks in the CPU sample of --impl reference")
     ap.add_argument("--no-checks", action="store_true", help="skip the oracle / sharding checks after the timed regions")
     ap.add_argument("--emulate-shard", default=None, metavar="R/N",
@@ -702,6 +739,9 @@ def main():
                 "note": "di_upload_counts + di_impute (multinet.py:217/:271 and :278-303); float64 [N, G] out like the "
                         "reference's DataFrame; the host-side pandas route needs several N x G float64 temporaries"}
             del imputed
+        if world == 1 and args.api and wl.get("raw") is not None:
+            eng.close()                                    # the API run builds its own engines
+            line["api"] = api_run(wl, args.epochs, local)
         if world == 1 and not args.no_cpu_baseline and wl["pred_idx"] is not None:
             # bounded: 2 sub-networks, at most ~15 s of Adam steps (the reference arm times 4 and the whole epoch)
             line["cpu_baseline"] = {k: v for k, v in cpu_reference(wl, args.epochs, n_sub=2, max_epoch_s=15.0).items()

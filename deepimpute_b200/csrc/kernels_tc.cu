@@ -58,7 +58,9 @@ struct TcParams {
     const SubnetDesc* desc;
     int S, H, O, Hp, Op;
     int n_cols;                 // UMMA N: batch rows (FWD*/BWD) or input-feature tile width (ADAM)
-    int tmem_cols;              // power of two >= n_cols
+    int tmem_cols;              // power of two >= (nacc + lo_acc) * n_cols
+    int nacc;                   // X3: accumulators the a b products of successive K blocks rotate through (>= 1) ...
+    int lo_acc;                 // ... and 1 if the small products a_lo b + a b_lo have an accumulator of their own (see acc_sum)
     int stages;                 // ring of raw (hi) slabs written by TMA
     int lo_stages;              // X3: ring of residual (lo) slabs written by the converter warps
     int which;                  // ADAM: 1 = W1 (in = X, dout = dz1), 2 = W2 (in = h, dout = dz2)
@@ -135,6 +137,31 @@ __device__ __forceinline__ uint32_t idesc_for(int n_cols, bool a_mn, bool b_mn) 
 // residual of the tensor core's operand truncation: a - (a with the low 13 mantissa bits cleared)
 __device__ __forceinline__ float tf32_residual(float a) {
     return a - __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+}
+
+// Short accumulation chains.  The tensor core adds every product into its fp32 accumulator with TRUNCATION: a chain of n
+// MMAs into one accumulator is biased by about n/2 ulp of the accumulator (measured: 17 K blocks x 12 MMAs = 204 MMAs
+// leave FWD1 1.2e-5 from the fp32 sum, and ReLU gates + Adam's m / sqrt(v) amplify that into a tail of 1e-3 deviations
+// after a few hundred steps; the same products summed by four CTAs of 51 MMAs each stay within 1e-5 of the fp32 path,
+// profiles/r02e_accumulation.md).  So the compensated kernels never build one long chain: the a b products of K block kb
+// go to accumulator kb % nacc, the small products a_lo b + a b_lo -- two thirds of all MMAs, 2^-11 of the magnitude --
+// to an accumulator of their own where their truncation is invisible, and the epilogue adds the nacc + 1 tiles in fp32.
+// taddr: lane base of the first accumulator; accumulator a sits n_cols columns further per step, the small-product
+// accumulator after the nacc-th; `used` = min(nacc, K blocks issued) accumulators hold data
+__device__ __forceinline__ void acc_sum16(uint32_t taddr, int c, int n_cols, int nacc, int used, bool lo_used, float (&v)[16]) {
+    tmem_ld16(taddr + c, v);
+    for (int a = 1; a < used; ++a) {
+        float t[16];
+        tmem_ld16(taddr + a * n_cols + c, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += t[i];
+    }
+    if (lo_used) {
+        float t[16];
+        tmem_ld16(taddr + nacc * n_cols + c, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += t[i];
+    }
 }
 
 // softplus and sigmoid of z from one exponential (output layer, multinet.py:145, and its derivative)
@@ -387,19 +414,24 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                     const uint32_t idesc_ts = idesc_for(p.n_cols, false, false);
                     const uint32_t sb_lo = smem_u32(lo_base + (size_t)ls * lo_stage_bytes);
                     const uint32_t ta = tmem + (uint32_t)(p.ts_acol0 + ls * TS_COLS);
+                    // short chains (see acc_sum16): a b -> accumulator kb % nacc, the small products -> their own one
+                    const uint32_t d_hi = tmem + (uint32_t)((kb % p.nacc) * p.n_cols);
+                    const uint32_t d_lo = tmem + (uint32_t)(p.nacc * p.n_cols);
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
-                        umma_tf32_ts(tmem, ta + BLOCK_K + j * UMMA_K, stage_desc<false>(sb, j), idesc_ts, (kb | j) ? 1u : 0u);
-                        umma_tf32_ts(tmem, ta + j * UMMA_K, stage_desc<false>(sb_lo, j), idesc_ts, 1u);
-                        umma_tf32_ts(tmem, ta + j * UMMA_K, stage_desc<false>(sb, j), idesc_ts, 1u);
+                        umma_tf32_ts(d_lo, ta + BLOCK_K + j * UMMA_K, stage_desc<false>(sb, j), idesc_ts, (kb | j) ? 1u : 0u);
+                        umma_tf32_ts(d_lo, ta + j * UMMA_K, stage_desc<false>(sb_lo, j), idesc_ts, 1u);
+                        umma_tf32_ts(d_hi, ta + j * UMMA_K, stage_desc<false>(sb, j), idesc_ts, (kb >= p.nacc || j) ? 1u : 0u);
                     }
                 } else if constexpr (X3) {
                     const uint32_t sa_lo = smem_u32(lo_base + (size_t)ls * stage_bytes), sb_lo = sa_lo + A_STAGE_BYTES;
+                    const uint32_t d_hi = tmem + (uint32_t)((kb % p.nacc) * p.n_cols);
+                    const uint32_t d_lo = tmem + (uint32_t)(p.nacc * p.n_cols);
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
-                        umma_tf32(tmem, stage_desc<A_MN>(sa_lo, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
-                        umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb_lo, j), idesc, 1u);
-                        umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, 1u);
+                        umma_tf32(d_lo, stage_desc<A_MN>(sa_lo, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                        umma_tf32(d_lo, stage_desc<A_MN>(sa, j), stage_desc<false>(sb_lo, j), idesc, 1u);
+                        umma_tf32(d_hi, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, (kb >= p.nacc || j) ? 1u : 0u);
                     }
                 } else {
 #pragma unroll
@@ -455,7 +487,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
             for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16];
                 __syncwarp();
-                tmem_ld16(taddr + c, v);
+                acc_sum16(taddr, c, ncol, p.nacc, min(p.nacc, nkb), X3 && p.lo_acc != 0, v);
                 if (!f_ok) continue;
                 // four independent Philox calls first (instruction-level parallelism), then the 16 activations
                 uint32_t w[4][4];
@@ -486,7 +518,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
             for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16], y[16];
                 __syncwarp();
-                tmem_ld16(taddr + c, v);
+                acc_sum16(taddr, c, ncol, p.nacc, min(p.nacc, nkb), X3 && p.lo_acc != 0, v);
                 if (!f_ok) continue;
                 if (p.aux_cols > 0) {
 #pragma unroll
@@ -551,7 +583,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
             for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16], h[16];
                 __syncwarp();
-                tmem_ld16(taddr + c, v);
+                acc_sum16(taddr, c, ncol, p.nacc, min(p.nacc, nkb), X3 && p.lo_acc != 0, v);
                 if (!f_ok) continue;
                 if (p.aux_cols > 0) {
 #pragma unroll
@@ -745,11 +777,21 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
                 if (kb < 40) DI_TRACE(48 + kb);
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                 const uint32_t sa_lo = sa + A_STAGE_BYTES, sb = sa + 2 * A_STAGE_BYTES, sb_lo = sb + b_bytes;
+                // short chains (see acc_sum16): a b -> accumulator kb % nacc, the small products -> their own one
+                const uint32_t d_hi = tmem + (uint32_t)((kb % p.nacc) * p.n_cols);
+                const uint32_t d_lo = p.lo_acc ? tmem + (uint32_t)(p.nacc * p.n_cols) : d_hi;
+                const bool fresh_hi = kb < p.nacc;            // first K block of this accumulator
 #pragma unroll
                 for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
-                    umma_tf32(tmem, stage_desc<A_MN>(sa_lo, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
-                    umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb_lo, j), idesc, 1u);
-                    umma_tf32(tmem, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, 1u);
+                    if (p.lo_acc) {
+                        umma_tf32(d_lo, stage_desc<A_MN>(sa_lo, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                        umma_tf32(d_lo, stage_desc<A_MN>(sa, j), stage_desc<false>(sb_lo, j), idesc, 1u);
+                        umma_tf32(d_hi, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, (!fresh_hi || j) ? 1u : 0u);
+                    } else {
+                        umma_tf32(d_hi, stage_desc<A_MN>(sa_lo, j), stage_desc<false>(sb, j), idesc, (!fresh_hi || j) ? 1u : 0u);
+                        umma_tf32(d_hi, stage_desc<A_MN>(sa, j), stage_desc<false>(sb_lo, j), idesc, 1u);
+                        umma_tf32(d_hi, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, 1u);
+                    }
                 }
                 umma_commit(&empty_bar[st]);
             }
@@ -804,7 +846,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
             for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16];
                 __syncwarp();
-                if (nkb > 0) tmem_ld16(taddr + c, v);
+                if (nkb > 0) acc_sum16(taddr, c, ncol, p.nacc, min(p.nacc, nkb), p.lo_acc != 0, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) mine[(int64_t)(c + i) * TILE_M] = nkb > 0 ? v[i] : 0.f;
             }
@@ -836,7 +878,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
                     for (int i = 0; i < 16; ++i) v[i] += __ldcg(src + (int64_t)i * TILE_M);
                 }
             } else {
-                tmem_ld16(taddr + c, v);
+                acc_sum16(taddr, c, ncol, p.nacc, min(p.nacc, nkb), p.lo_acc != 0, v);
             }
         };
 
@@ -1109,12 +1151,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
                 const int cnt = min(KG, nkb - (pi % ppr) * KG);
                 mbar_wait(&ops_bar, pi & 1, 6);
                 tc_fence_after();
+                // X3: round 1 (dout_hi in_hi) accumulates in columns [0, n_cols), rounds 0 and 2 (the small products) in
+                // [n_cols, 2 n_cols): short chains, see acc_sum16
+                const int round = pi / ppr;
+                const uint32_t dst = (X3 && round != 1) ? tmem + (uint32_t)p.n_cols : tmem;
+                const bool fresh = (pi % ppr) == 0 && (!X3 || round < 2);       // first pass of this accumulator
                 for (int k = 0; k < cnt; ++k) {
                     const uint32_t sa = smem_u32(sA + (size_t)k * A_STAGE_BYTES);
                     const uint32_t sb = smem_u32(sB + (size_t)k * b_block_bytes);
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
-                        umma_tf32(tmem, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (pi | k | j) ? 1u : 0u);
+                        umma_tf32(dst, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (!fresh || k || j) ? 1u : 0u);
                 }
                 if (pi + 1 < npass) umma_commit(&mma_bar);
             }
@@ -1137,6 +1184,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
             float g[AD_R];
             __syncwarp();
             tmem_ld8(taddr + c * AD_R, g);
+            if constexpr (X3) {
+                float gl[AD_R];
+                tmem_ld8(taddr + p.n_cols + c * AD_R, gl);
+#pragma unroll
+                for (int r = 0; r < AD_R; ++r) g[r] += gl[r];
+            }
             mbar_wait(&wfull[st], (c / ring) & 1, 7);
             if (c < 40) DI_TRACE_T0(8 + c);
             if (f_ok) {
@@ -1357,23 +1410,28 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
     } else if (warp == 4 * ngroups + 1) {
         if (elect_one()) {
             const uint32_t idesc = idesc_for(p.n_cols, true, true);
-            auto mma_round = [&](const uint8_t* a, const uint8_t* b, bool first) {
+            auto mma_round = [&](uint32_t dst, const uint8_t* a, const uint8_t* b, bool first) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     const uint32_t sa = smem_u32(a + (size_t)kb * A_STAGE_BYTES);
                     const uint32_t sb = smem_u32(b + (size_t)kb * A_STAGE_BYTES);
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
-                        umma_tf32(tmem, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (!first || kb || j) ? 1u : 0u);
+                        umma_tf32(dst, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (!first || kb || j) ? 1u : 0u);
                 }
             };
+            // X3: the hi hi product and the two small products accumulate separately (columns [0, 128) and [128, 256),
+            // see acc_sum16); the epilogue adds the two tiles
+            const uint32_t d_lo = tmem + (uint32_t)ADAM_TILE;
             mbar_wait(&ops_bar[0], 0, 6);
             tc_fence_after();
-            mma_round(set0, set1, true);                               // dout_hi in_lo   (plain TF32: dout in)
             if constexpr (X3) {
-                mma_round(set0, set2, false);                          // dout_hi in_hi
+                mma_round(d_lo, set0, set1, true);                     // dout_hi in_lo
+                mma_round(tmem, set0, set2, true);                     // dout_hi in_hi
                 mbar_wait(&ops_bar[1], 0, 6);
                 tc_fence_after();
-                mma_round(set3, set2, false);                          // dout_lo in_hi
+                mma_round(d_lo, set3, set2, false);                    // dout_lo in_hi
+            } else {
+                mma_round(tmem, set0, set1, true);                     // dout in
             }
             umma_commit(&tmem_full_bar);
         }
@@ -1398,6 +1456,12 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
             float g[AD_R];
             __syncwarp();
             tmem_ld8(taddr + c * AD_R, g);
+            if constexpr (X3) {
+                float gl[AD_R];
+                tmem_ld8(taddr + ADAM_TILE + c * AD_R, gl);
+#pragma unroll
+                for (int r = 0; r < AD_R; ++r) g[r] += gl[r];
+            }
             mbar_wait(&wfull[c], 0, 7);
             if (tracer && c < 40) p.trace[8 + c] = clock64();
             __syncwarp();
@@ -1425,210 +1489,6 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
     DI_TRACE_T0(5);
 }
 
-// --------------------------------------------------------------------------- ADAM, one CTA per SM, 128-bit epilogue
-// Same tile, operands and arithmetic as tc_adam_big_kernel with the two MMA operands SWAPPED: A = `in`, B = `dout`
-// (both are [32 k][128] MN-major tiles of one layout, so the swap is free), which puts the tile's INPUT rows on the 128
-// TMEM lanes and its OUTPUT features -- the contiguous dimension of W[in][out] -- on the accumulator columns.  A thread
-// then owns one weight row and consecutive features: w, m, v arrive as 128-bit shared loads and leave (with W_lo) as
-// 128-bit global stores.  The epilogue of tc_adam_big_kernel issues 56 32-bit memory instructions per 8 weights and is
-// bound by the issue rate of the load/store unit (about 1000 warp instructions per 2000 cycles, traces r02b); here it
-// is 14 per 8 weights.
-//   chunk g (0..3) = features [32 g, 32 g + 32) x 128 rows x {w, m, v}: 3 x 16 KB, delivered by TMA as 32-row boxes with
-//   the 128-byte swizzle (a thread reads its own 128-byte row: chunk j of row r sits at j ^ (r & 7), so the 128-bit
-//   loads of a quarter warp hit eight different bank groups); the first `ad_nded` chunks have dedicated stages filled
-//   while the MMAs run, the others land in the operand area once the accumulator is complete.
-//   warp (q, g): TMEM lane quadrant q = rows 32 q .., feature chunk g; 16 epilogue warps + TMA warp + MMA warp.
-struct AdamVecMaps { CUtensorMap A, B, Alo, Blo, W, M, V; };   // dout, in, twins; w / m / v as [32 rows][32 features] swizzled boxes
-constexpr int ADV_CHUNK_BYTES = 3 * TILE_M * 32 * 4;      // 48 KB
-
-template <bool X3>
-__global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_vec_kernel(const __grid_constant__ AdamVecMaps maps1,
-                                                                       const __grid_constant__ AdamVecMaps maps2, const TcParams p) {
-    const int s = blockIdx.z + p.s_base;
-    const SubnetDesc d = p.desc[s];
-    const bool second = (int)blockIdx.x >= p.nx1;
-    const AdamVecMaps* mp = second ? &maps2 : &maps1;
-    const CUtensorMap &mapA = mp->A, &mapB = mp->B, &mapAlo = mp->Alo, &mapBlo = mp->Blo, &mapW = mp->W, &mapM = mp->M, &mapV = mp->V;
-    const int m0 = blockIdx.y * TILE_M;                    // first output feature of the tile
-    const int n0 = ((int)blockIdx.x - (second ? p.nx1 : 0)) * ADAM_TILE;   // first input row of the tile
-    int out_dim, in_dim, a_c0, b_c0, b_c1;
-    int64_t row_base;
-    if (!second) { out_dim = p.Hp; in_dim = d.Pp; a_c0 = s * p.Hp + m0; b_c0 = (int)d.coff + n0; b_c1 = (int)p.row0; row_base = d.coff; }
-    else { out_dim = p.Op; in_dim = p.Hp; a_c0 = s * p.Op + m0; b_c0 = s * p.Hp + n0; b_c1 = 0; row_base = (int64_t)s * p.Hp; }
-    if (m0 >= out_dim || n0 >= in_dim) return;
-    const int nkb = p.nkb_adam;
-    const int rows_ok = min(ADAM_TILE, in_dim - n0);       // multiple of 32
-    const int nrb = rows_ok / 32;                          // 32-row boxes per chunk and tensor
-    const int nfc = min(4, (out_dim - m0) / 32);           // 32-feature chunks of this tile (out_dim is a multiple of 32)
-
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int NSETS = X3 ? 4 : 2;
-    const uint32_t set_bytes = (uint32_t)nkb * A_STAGE_BYTES;
-    uint8_t* set0 = smem;                                           // dout_hi
-    uint8_t* set1 = smem + set_bytes;                               // in_lo   (plain TF32: in)
-    uint8_t* set2 = smem + 2 * (size_t)set_bytes;                   // in_hi
-    uint8_t* set3 = smem + 3 * (size_t)set_bytes;                   // dout_lo
-    uint8_t* ded = smem + (size_t)NSETS * set_bytes;
-    auto stage_ptr = [&](int g) -> uint8_t* {
-        return g < p.ad_nded ? ded + (size_t)g * ADV_CHUNK_BYTES : smem + (size_t)(g - p.ad_nded) * ADV_CHUNK_BYTES;
-    };
-    __shared__ uint64_t ops_bar[2], tmem_full_bar, wfull[4];
-    __shared__ uint32_t tmem_base_slot;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int TMA_WARP = 4 * AD_MAX_GROUPS, MMA_WARP = TMA_WARP + 1;
-    DI_TRACE_T0(0);
-    if (threadIdx.x == 0) {
-        mbar_init(&ops_bar[0], 1); mbar_init(&ops_bar[1], 1); mbar_init(&tmem_full_bar, 1);
-        for (int i = 0; i < 4; ++i) mbar_init(&wfull[i], 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_base_slot;
-    if (warp != TMA_WARP) pdl_wait();
-    if (p.pdl_early && threadIdx.x == 0) pdl_release();
-    __syncwarp();
-
-    if (warp == TMA_WARP) {
-        if (elect_one()) {
-            auto load_set = [&](const CUtensorMap* m, uint8_t* dst, uint64_t* bar, int c0, int c1) {
-                for (int kb = 0; kb < nkb; ++kb)
-                    load_stage<true>(dst + (size_t)kb * A_STAGE_BYTES, m, bar, c0, c1 + kb * BLOCK_K, TILE_M);
-            };
-            auto load_chunk = [&](int g) {
-                uint8_t* st = stage_ptr(g);
-                mbar_arrive_expect_tx(&wfull[g], 3u * (uint32_t)nrb * 4096u);
-                const int32_t c0 = m0 + 32 * g;
-                for (int rb = 0; rb < nrb; ++rb) {
-                    const int32_t r = (int32_t)(row_base + n0 + 32 * rb);
-                    tma_load_2d(st + rb * 4096, &mapW, &wfull[g], c0, r);
-                    tma_load_2d(st + 16384 + rb * 4096, &mapM, &wfull[g], c0, r);
-                    tma_load_2d(st + 32768 + rb * 4096, &mapV, &wfull[g], c0, r);
-                }
-            };
-            // ADAM follows BWD, which writes dz1 (the `dout` of the W1 tiles) and nothing else this kernel reads
-            const bool a_free = p.pdl_prefetch && second;
-            const bool early = p.pdl_prefetch != 0;
-            if constexpr (X3) {
-                mbar_arrive_expect_tx(&ops_bar[0], 3u * set_bytes);
-                mbar_arrive_expect_tx(&ops_bar[1], set_bytes);
-            } else {
-                mbar_arrive_expect_tx(&ops_bar[0], 2u * set_bytes);
-            }
-            auto load_in = [&]() {
-                if constexpr (X3) { load_set(&mapBlo, set1, &ops_bar[0], b_c0, b_c1); load_set(&mapB, set2, &ops_bar[0], b_c0, b_c1); }
-                else load_set(&mapB, set1, &ops_bar[0], b_c0, b_c1);
-            };
-            auto load_dout = [&]() {
-                load_set(&mapA, set0, &ops_bar[0], a_c0, 0);
-                if constexpr (X3) load_set(&mapAlo, set3, &ops_bar[1], a_c0, 0);
-            };
-            if (early) {
-                load_in();
-                if (a_free) load_dout();
-                for (int g = 0; g < min(p.ad_nded, nfc); ++g) load_chunk(g);
-                pdl_wait();
-                if (!a_free) load_dout();
-            } else {
-                pdl_wait();
-                load_dout(); load_in();
-                for (int g = 0; g < min(p.ad_nded, nfc); ++g) load_chunk(g);
-            }
-            if (nfc > p.ad_nded) {                                 // the operand area becomes chunk stages
-                mbar_wait(&tmem_full_bar, 0, 4);
-                for (int g = p.ad_nded; g < nfc; ++g) load_chunk(g);
-            }
-        }
-    } else if (warp == MMA_WARP) {
-        if (elect_one()) {
-            const uint32_t idesc = idesc_for(TILE_M, true, true);      // M = 128 input rows, N = 128 output features
-            auto mma_round = [&](const uint8_t* in_t, const uint8_t* dout_t, bool first) {
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const uint32_t sa = smem_u32(in_t + (size_t)kb * A_STAGE_BYTES);
-                    const uint32_t sb = smem_u32(dout_t + (size_t)kb * A_STAGE_BYTES);
-#pragma unroll
-                    for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
-                        umma_tf32(tmem, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (!first || kb || j) ? 1u : 0u);
-                }
-            };
-            mbar_wait(&ops_bar[0], 0, 6);
-            tc_fence_after();
-            mma_round(set1, set0, true);                               // in_lo dout_hi   (plain TF32: in dout)
-            if constexpr (X3) {
-                mma_round(set2, set0, false);                          // in_hi dout_hi
-                mbar_wait(&ops_bar[1], 0, 6);
-                tc_fence_after();
-                mma_round(set2, set3, false);                          // in_hi dout_lo
-            }
-            umma_commit(&tmem_full_bar);
-        }
-    } else {
-        const int quad = warp & 3, g = warp >> 2;          // TMEM lane quadrant (rows 32 quad ..), feature chunk
-        const int r = quad * 32 + lane;                    // input row inside the tile
-        const bool row_ok = r < rows_ok;
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * g);
-        const AdamParams adam = adam_of(p);
-        DI_TRACE_T0(2);
-        mbar_wait(&tmem_full_bar, 0, 4);
-        tc_fence_after();
-        if (threadIdx.x == 0 && !p.pdl_early) pdl_release();
-        __syncwarp();
-        DI_TRACE_T0(3);
-        if (g < nfc) {
-            mbar_wait(&wfull[g], 0, 7);
-            if (p.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[8] = clock64();
-            __syncwarp();
-            // this thread's 128-byte row of the chunk: box rb = r / 32, row r % 32, 16-byte piece j at j ^ (r & 7)
-            const uint32_t rowb = smem_u32(stage_ptr(g)) + (uint32_t)(r >> 5) * 4096u + (uint32_t)(r & 31) * 128u;
-            const uint32_t sw = (uint32_t)(r & 7);
-            const int64_t off = (row_base + n0 + r) * (int64_t)out_dim + m0 + 32 * g;
-            float* gw = (second ? p.W2 : p.W1) + off;
-            float* gm = (second ? p.mW2 : p.mW1) + off;
-            float* gv = (second ? p.vW2 : p.vW1) + off;
-            float* gl0 = second ? p.W2lo : p.W1lo;
-            float* gl = gl0 ? gl0 + off : nullptr;
-#pragma unroll
-            for (int sub = 0; sub < 4; ++sub) {            // 8 features per pass
-                float acc[8];
-                __syncwarp();
-                tmem_ld8(taddr + 8 * sub, acc);
-                if (!row_ok) continue;
-                float w[8], m[8], v[8];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t a = rowb + (((uint32_t)(2 * sub + h) ^ sw) << 4);
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w[4 * h]), "=f"(w[4 * h + 1]), "=f"(w[4 * h + 2]), "=f"(w[4 * h + 3]) : "r"(a));
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(m[4 * h]), "=f"(m[4 * h + 1]), "=f"(m[4 * h + 2]), "=f"(m[4 * h + 3]) : "r"(a + 16384u));
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * h]), "=f"(v[4 * h + 1]), "=f"(v[4 * h + 2]), "=f"(v[4 * h + 3]) : "r"(a + 32768u));
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) adam_update_fast(acc[i], w[i], m[i], v[i], adam);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int o = 8 * sub + 4 * h;
-                    *reinterpret_cast<float4*>(gw + o) = make_float4(w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]);
-                    *reinterpret_cast<float4*>(gm + o) = make_float4(m[4 * h], m[4 * h + 1], m[4 * h + 2], m[4 * h + 3]);
-                    *reinterpret_cast<float4*>(gv + o) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
-                    if (gl) *reinterpret_cast<float4*>(gl + o) = make_float4(tf32_residual(w[4 * h]), tf32_residual(w[4 * h + 1]),
-                                                                          tf32_residual(w[4 * h + 2]), tf32_residual(w[4 * h + 3]));
-                }
-            }
-            if (p.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[48] = clock64();
-        }
-        __syncwarp();
-        DI_TRACE_T0(4);
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
-    DI_TRACE_T0(5);
-}
-
 // ------------------------------------------------------------------------------------------------ host side
 struct TcState {
     // weights / step buffers (fixed for the life of the engine)
@@ -1643,15 +1503,13 @@ struct TcState {
     CUtensorMap Xstep_k, Xstep_mn, Ystep_aux;
     CUtensorMap Xchunk_k, Hchunk_k;                        // inference chunk
     CUtensorMap W1_t[3], W2_t[3];                          // {w, m, v} tiles of the ADAM epilogue
-    CUtensorMap W1_v[3], W2_v[3];                          // ... as [32 rows][32 features] swizzled boxes (tc_adam_vec_kernel)
-    bool adam_vec = false;                                 // 128-bit ADAM epilogue (DEEPIMPUTE_B200_ADAM_VEC=0: the 32-bit one)
-    int adv_nded = 0, smem_adam_vec = 0;
     // LT kernels (every operand by TMA): residual twins of the weights and K-major views of the activation twins
     bool lt = false;                                       // DEEPIMPUTE_B200_LT=0 selects the converter-warp kernels
     CUtensorMap W1lo_mn, W2lo_mn, W2lo_k, Hlo_k, DZ2lo_k, Xstep_lo_k, Xtr_lo_k, Xte_lo_k, Xchunk_lo_k, Hchunk_lo_k;
     struct LtCfg { int stages = 0, smem = 0; bool aux = false; };
     LtCfg lt_train, lt_train_noaux, lt_infer;
     int lt_ks = 1;                                         // split-K factor of FWD1 / BWD (1: one CTA walks the whole K loop)
+    int nacc_ts = 1;                                       // accumulators of the TS kernels (their weight slabs share tensor memory)
     float* kpart[2] = {nullptr, nullptr};                  // scratch tiles of FWD1 / BWD: [S][m_tiles][lt_ks][Bp][128]
     unsigned int* kcount[2] = {nullptr, nullptr};          // arrival counters [S][m_tiles]
     // L2 residency of the optimiser state (DEEPIMPUTE_B200_L2_PERSIST): access-policy window of the training launches
@@ -1729,6 +1587,7 @@ TcParams base_params(Engine& e) {
     const double r = e.cfg.dropout_rate;
     p.drop_thresh = r > 0.0 ? (uint32_t)(r * 4294967296.0) : 0u;
     p.keep_scale = 1.0f;
+    p.nacc = 1; p.lo_acc = 0;
     return p;
 }
 
@@ -1823,8 +1682,7 @@ bool tc_init(Engine& e) {
     for (int i = 0; i < 3; ++i) {
         ok = ok && make_map_plain(&st->W1_t[i], w1[i], e.PT, e.Hp, e.Hp, st->wbox1, AD_R);
         ok = ok && make_map_plain(&st->W2_t[i], w2[i], SH, e.Op, e.Op, st->wbox2, AD_R);
-        ok = ok && make_map_2d(&st->W1_v[i], w1[i], e.PT, e.Hp, e.Hp, 32);
-        ok = ok && make_map_2d(&st->W2_v[i], w2[i], SH, e.Op, e.Op, 32);
+
     }
     if (!ok) { e.err = "cuTensorMapEncodeTiled failed"; return false; }
     // shared-memory budgets.  The side-operand tile (aux) is dropped for the compensated FWD2, whose doubled slabs
@@ -1858,12 +1716,15 @@ bool tc_init(Engine& e) {
     if (st->x3) {
         if (const char* v = getenv("DEEPIMPUTE_B200_TS")) st->ts = atoi(v) != 0;
         const int nb = e.Bp * BLOCK_K * 4;
-        st->ts_acol0 = (e.Bp + 31) / 32 * 32;
         for (int hs = 6; hs >= 2 && st->ts; --hs) {
             const int ls = std::min(hs, 4);
             const int bytes1 = hs * ((int)A_STAGE_BYTES + nb) + ls * nb + 1024, bytes2 = bytes1 + aux_floats * 4;
-            if (bytes2 <= 224 * 1024 && st->ts_acol0 + ls * TS_COLS <= 512) {
+            // tensor memory: nacc + 1 accumulators (short chains, acc_sum16) in front of the ls weight slabs
+            const int nacc = std::min(4, (512 - ls * TS_COLS) / e.Bp - 1);
+            if (bytes2 <= 224 * 1024 && nacc >= 1) {
                 st->ts_stages = hs; st->ts_lo = ls; st->ts_smem1 = bytes1; st->ts_smem2 = bytes2;
+                st->nacc_ts = nacc;
+                st->ts_acol0 = (nacc + 1) * e.Bp;
                 st->ts_tmem = pow2_cols(st->ts_acol0 + ls * TS_COLS);
                 break;
             }
@@ -1986,11 +1847,7 @@ bool tc_init(Engine& e) {
         st->adam_big = st->ad_nded >= 1 && (AD_MAX_CHUNKS - st->ad_nded) * st->ad_stride <= ops;
         st->smem_adam_big = ops + st->ad_nded * st->ad_stride + 1024;
         if (const char* v = getenv("DEEPIMPUTE_B200_ADAM")) if (!strcmp(v, "ring")) st->adam_big = false;
-        // 128-bit epilogue: 4 chunks of 48 KB, `adv_nded` of them in dedicated stages, the rest in the operand area
-        st->adv_nded = room > 0 ? std::min(4, room / ADV_CHUNK_BYTES) : 0;
-        st->adam_vec = st->adam_big && (4 - st->adv_nded) * ADV_CHUNK_BYTES <= ops;
-        st->smem_adam_vec = ops + st->adv_nded * ADV_CHUNK_BYTES + 1024;
-        if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_VEC")) st->adam_vec = st->adam_vec && atoi(v) != 0;
+
         if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_GROUPS")) st->ad_groups = std::max(1, std::min(AD_MAX_GROUPS, atoi(v)));
     }
     if (st->smem_adam > 227 * 1024 || !st->fwd1_train[0].stages || !st->fwd2_train[0].stages || !st->bwd_train[0].stages ||
@@ -2026,10 +1883,7 @@ bool tc_init(Engine& e) {
         set((const void*)tc_adam_big_kernel<false>, st->smem_adam_big);
         set((const void*)tc_adam_big_kernel<true>, st->smem_adam_big);
     }
-    if (st->adam_vec) {
-        set((const void*)tc_adam_vec_kernel<false>, st->smem_adam_vec);
-        set((const void*)tc_adam_vec_kernel<true>, st->smem_adam_vec);
-    }
+
     if (ce != cudaSuccess) { e.err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return false; }
     return true;
 }
@@ -2113,6 +1967,14 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     const CUtensorMap& Yaux = which_x == 0 ? st->Ytr_aux : st->Ystep_aux;
     TcParams p = base_params(e);
     p.n_cols = e.Bp; p.tmem_cols = pow2_cols(e.Bp);
+    if (st->x3) {
+        // short accumulation chains (acc_sum16): up to four a b accumulators + one for the small products; kernels that
+        // may share an SM (pl.deep == 0: two CTAs per SM) stay within half of the 512 columns
+        const int budget = (st->lt || pl.deep != 0) ? 512 : 256;
+        p.lo_acc = 2 * e.Bp <= budget ? 1 : 0;
+        p.nacc = std::max(1, std::min(4, budget / e.Bp - p.lo_acc));
+        p.tmem_cols = pow2_cols((p.nacc + p.lo_acc) * e.Bp);
+    }
     p.row0 = a.row0; p.rows_per_block_y = 0;
     p.Y = a.Y; p.ldy = a.ldy; p.Hact = e.Hact; p.ldh = (int64_t)e.S * e.Hp; p.DZ2 = e.DZ2; p.DZ1 = e.DZ1;
     p.Hlo = e.Hlo; p.DZ2lo = e.DZ2lo; p.DZ1lo = e.DZ1lo;          // null unless DI_MATH_TF32X3
@@ -2155,7 +2017,7 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
       q.stages = c1.stages; q.lo_stages = c1.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace;
       if (st->ts) {
-          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.ts_wbox = st->wbox1;
+          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.nacc = st->nacc_ts; q.lo_acc = 1; q.ts_wbox = st->wbox1;
           launch_on<TC_FWD1, true, true>(e, pl, "fwd1", st->W1_ts, Xk, Xk, q, dim3(1, mh, pl.ns), st->ts_smem1);
       } else if (st->x3) launch_on<TC_FWD1, true>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem);
       else launch_on<TC_FWD1, false>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem); }
@@ -2163,7 +2025,7 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
       q.stages = c2.stages; q.lo_stages = c2.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 256;
       if (c2.aux) { q.aux_cols = st->aux_y; q.aux_row0 = a.row0; }
       if (st->ts) {
-          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.ts_wbox = st->wbox2;
+          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.nacc = st->nacc_ts; q.lo_acc = 1; q.ts_wbox = st->wbox2;
           q.aux_cols = st->aux_y; q.aux_row0 = a.row0;
           launch_on<TC_FWD2, true, true>(e, pl, "fwd2", st->W2_ts, st->H_k, Yaux, q, dim3(1, mo, pl.ns), st->ts_smem2);
       } else if (st->x3) launch_on<TC_FWD2, true>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem);
@@ -2172,7 +2034,7 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
       if (c3.aux) { q.aux_cols = st->aux_h; q.aux_row0 = 0; }
       q.stages = c3.stages; q.lo_stages = c3.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 512;
       if (st->ts_bwd) {
-          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.ts_wbox = TILE_M;
+          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.nacc = st->nacc_ts; q.lo_acc = 1; q.ts_wbox = TILE_M;
           q.aux_cols = st->aux_h; q.aux_row0 = 0;
           launch_on<TC_BWD, true, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), st->ts_smem2);
       } else if (st->x3) launch_on<TC_BWD, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem);
@@ -2180,7 +2042,7 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     }
     if (st->simt_adam && !pl.graph) { simt_adam_only(e, a); return; }
     TcParams q = p;
-    q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;
+    q.n_cols = ADAM_TILE; q.tmem_cols = st->x3 ? 2 * ADAM_TILE : ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;   // X3: a b and the small products apart
     q.row0 = a.row0; q.wbox = st->wbox1; q.wbox2 = st->wbox2;
     q.W1 = e.W1; q.mW1 = e.mW1; q.vW1 = e.vW1; q.W2 = e.W2; q.mW2 = e.mW2; q.vW2 = e.vW2;
     q.W1lo = st->lt ? e.W1lo : nullptr; q.W2lo = st->lt ? e.W2lo : nullptr;
@@ -2201,15 +2063,7 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam");
     q.ad_nded = st->ad_nded; q.ad_stride = st->ad_stride; q.ad_kg = st->ad_kg;
     { static const bool generic = [] { const char* v = getenv("DEEPIMPUTE_B200_ADAM_GENERIC"); return v && atoi(v) != 0; }(); q.ad_generic = generic ? 1 : 0; }
-    if (st->adam_vec) {
-        AdamVecMaps v1, v2;
-        v1.A = m1.A; v1.B = m1.B; v1.Alo = m1.Alo; v1.Blo = m1.Blo; v1.W = st->W1_v[0]; v1.M = st->W1_v[1]; v1.V = st->W1_v[2];
-        v2.A = m2.A; v2.B = m2.B; v2.Alo = m2.Alo; v2.Blo = m2.Blo; v2.W = st->W2_v[0]; v2.M = st->W2_v[1]; v2.V = st->W2_v[2];
-        q.ad_nded = st->adv_nded;
-        const bool pdl = st->pdl && pl.graph;
-        if (st->x3) launch_k(tc_adam_vec_kernel<true>, grid, NTHREADS_BIG, st->smem_adam_vec, pl.main, pdl, v1, v2, q);
-        else launch_k(tc_adam_vec_kernel<false>, grid, NTHREADS_BIG, st->smem_adam_vec, pl.main, pdl, v1, v2, q);
-    } else if (st->adam_big) {
+    if (st->adam_big) {
         const int nthreads = (4 * st->ad_groups + 2) * 32;
         const bool pdl = st->pdl && pl.graph;
         if (st->x3) launch_k(tc_adam_big_kernel<true>, grid, nthreads, st->smem_adam_big, pl.main, pdl, m1, m2, q);
@@ -2351,7 +2205,7 @@ const char* tc_describe(Engine& e) {
              "fwd/bwd=%s splitk=%d stages=%d/%d adam=%s groups=%d graph=%d pdl=%d%s l2_window=%d (%.1f MB of %.1f MB state, hitRatio %.2f) graph_fallbacks=%lld",
              st->lt ? "lt" : (st->ts ? "ts" : (st->x3 ? "x3-smem" : "tf32")), st->lt ? st->lt_ks : 1,
              st->lt ? st->lt_train.stages : st->fwd1_train[1].stages, st->lt ? st->lt_infer.stages : st->infer.stages,
-             st->adam_vec ? "resident-128bit" : (st->adam_big ? "resident" : "ring"), st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0,
+             st->adam_big ? "resident" : "ring", st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0,
              st->pdl_early_adam ? "(early release, all four kernels)" : (st->pdl_early ? "(early release, fwd/bwd)" : ""), st->l2_window ? 1 : 0,
              st->l2_window ? st->l2_policy.num_bytes * (double)st->l2_policy.hitRatio / 1048576.0 : 0.0,
              e.state_bytes / 1048576.0, st->l2_window ? (double)st->l2_policy.hitRatio : 0.0, (long long)st->graph_fallbacks);
@@ -2369,6 +2223,11 @@ void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_va
     const CUtensorMap& Xk = which_x == 2 ? st->Xte_k : st->Xchunk_k;
     TcParams p = base_params(e);
     p.n_cols = e.infer_tile; p.tmem_cols = e.infer_tile; p.stages = st->infer.stages; p.lo_stages = st->infer.lo_stages;
+    if (st->x3) {        // accumulators as in training (one CTA per SM: all 512 columns)
+        p.lo_acc = 1;
+        p.nacc = std::max(1, std::min(4, 512 / e.infer_tile - 1));
+        p.tmem_cols = pow2_cols((p.nacc + 1) * e.infer_tile);
+    }
     p.rows_per_block_y = e.infer_tile;
     p.ldh = (int64_t)e.S * e.Hp;
     p.n_valid = (int)n_valid; p.training = 0; p.drop_thresh = 0;

@@ -127,6 +127,13 @@ class MultiNet:
         self.history = None
         self._owned = None            # sub-networks of every rank (parallel.assign_subnets); None = unsharded
 
+    def _phase(self, name, t0):
+        """Wall-clock seconds of one phase of fit / predict, accumulated in ``self.timings`` (bench.py --api)."""
+        import time as _time
+        now = _time.perf_counter()
+        self.timings[name] = self.timings.get(name, 0.0) + (now - t0)
+        return now
+
     def setCores(self, ncores):
         # kept for API compatibility (multinet.py:92-97); the GPU engine ignores it
         if ncores > 0:
@@ -249,7 +256,10 @@ class MultiNet:
             mode='random',
             ):
         """Select genes, partition them into sub-networks, train all of them on the GPU, record test metrics."""
+        import time as _time
+        tp = _time.perf_counter()
         inspect_data(raw)
+        tp = self._phase("fit_inspect_s", tp)
 
         if self.shard is not None and self.shard.distributed and self.seed is None:
             # every rank derives targets / predictors / the cell split from its own np.random stream: without a shared
@@ -265,7 +275,7 @@ class MultiNet:
         # pandas keeps a homogeneous frame gene-major, so ``raw.values`` is a transposed view: make the cell-major copy the
         # engine wants ONCE and hand the same array to every consumer (statistics, correlations, upload)
         raw_values = np.ascontiguousarray(raw.values)
-        import time as _time
+        tp = self._phase("fit_cell_major_copy_s", tp)
         t0 = _time.perf_counter()
         gpu_stats = self.stats_engine == "gpu" or (self.stats_engine == "auto" and raw_values.size >= 2e8)
         if gpu_stats:
@@ -316,6 +326,7 @@ class MultiNet:
         self.timings["predictor_selection_s"] = _time.perf_counter() - t0
         self.timings["predictor_engine"] = "gpu" if use_gpu else "host"
 
+        tp = _time.perf_counter()
         print("Normalization")
         on_device = self.postprocess == "gpu"
         if not on_device:
@@ -334,11 +345,13 @@ class MultiNet:
         targ_idx = cols.get_indexer(self.targets.reshape(-1)).reshape(self.targets.shape).astype(np.int32)
         mine = self._my_subnets(len(pred_idx))
 
+        tp = self._phase("fit_build_engine_s", tp)
         print("Fitting with {} cells".format(raw.shape[0]))
         if on_device:       # raw counts go up once; log1p -> float32 (multinet.py:217) happens in HBM
             model.set_counts(raw_values, [pred_idx[s] for s in mine], targ_idx[mine])
         else:
             model.set_data(norm_values, [pred_idx[s] for s in mine], targ_idx[mine])
+        tp = self._phase("fit_upload_s", tp)
         # Keras sums the per-branch losses and EarlyStopping watches the sum (multinet.py:242-243): when the
         # branches live on several GPUs the two scalars are summed over ranks before the stop decision
         exchange = None
@@ -352,9 +365,12 @@ class MultiNet:
         self.history = result.history
         self.trained_epochs = len(result.history['loss'])
         print("Stopped fitting after {} epochs".format(self.trained_epochs))
+        tp = self._phase("fit_epochs_s", tp)
+        self.timings["fit_epochs_device_ms"] = float(sum(getattr(result, "epoch_ms", []) or []))
 
         self.engine = model
         self.save(model)
+        tp = self._phase("fit_save_s", tp)
 
         # held-out metrics on originally non-zero entries (multinet.py:251-262)
         if on_device:       # only the held-out block is normalised on the host
@@ -368,6 +384,7 @@ class MultiNet:
             'correlation': pearsonr(y_true, y_hat)[0],
             'MSE': np.sum((y_true - y_hat) ** 2) / len(y_true)
         }
+        self._phase("fit_test_metrics_s", tp)
         return self
 
     def _set_partition(self, cols, raw_values, genes, cand, corr, ntop, mode):
@@ -403,6 +420,8 @@ class MultiNet:
                 imputed_only=False,
                 policy="restore"):
 
+        import time as _time
+        tp = _time.perf_counter()
         model = self.engine if self.engine is not None else self.load()
 
         cols = raw.columns
@@ -419,6 +438,7 @@ class MultiNet:
             # fused path: counts up once, log1p + forward + duplicate mean + clamp + expm1 + policy on the device,
             # one float64 [N, G] matrix back (multinet.py:271-303)
             model.set_counts(raw.values, [pred_idx[s] for s in mine], targ_idx[mine])
+            tp = self._phase("predict_upload_s", tp)
             if policy == "restore":
                 print("Filling zeros")
             elif policy == "max":
@@ -430,7 +450,9 @@ class MultiNet:
                 values = model.impute(policy=policy, pred=full, slot_gene=targ_pos)
             # the matrix is freshly allocated and owned by this call: wrap it, do not copy it (pandas would otherwise
             # duplicate all N x G float64 values: ~2 s per GB)
+            tp = self._phase("predict_impute_s", tp)
             imputed = pd.DataFrame(values, index=raw.index, columns=raw.columns, copy=False)
+            self._phase("predict_wrap_s", tp)
             if imputed_only:
                 return imputed.loc[:, np.unique(targets_flat)]
             return imputed
