@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/deepimpute_b200.h"
 
 namespace {
@@ -189,6 +191,7 @@ const char* di_corr_last_error(void) { return g_err.c_str(); }
 int di_corr_topk(int32_t device, const float* raw, int64_t n_cells, int64_t n_genes, const int32_t* cand, int64_t n_cand,
                  const int32_t* targ, int32_t n_subnets, int32_t sub_outputdim, int32_t ntop, int32_t* top_out,
                  float* val_out, float* device_ms_out) {
+    struct R { R() { nvtxRangePushA("di_corr_topk"); } ~R() { nvtxRangePop(); } } nvtx_range;
     int rc = DI_OK;
     if (!raw || !cand || !targ || !top_out || n_cells <= 1 || n_genes <= 0 || n_cand <= 0 || n_subnets <= 0 ||
         sub_outputdim <= 0 || ntop <= 0 || ntop > MAX_TOP) { g_err = "di_corr_topk: bad arguments"; return DI_ERR_ARG; }

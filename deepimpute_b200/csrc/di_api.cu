@@ -8,9 +8,18 @@
 #include <cstring>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges show up under a profiler, cost nothing without one
+
 #include "engine.h"
 
 using namespace di;
+
+namespace {
+struct NvtxRange {   // one range per C-ABI call of the path: upload / split / epoch / predict / impute
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
 
 struct di_handle { Engine e; };
 
@@ -355,6 +364,7 @@ static void drop_counts(Engine& e) {
 int di_upload_matrix(di_handle* h, const float* norm, int64_t n_cells, int64_t n_genes) {
     if (!h) return DI_ERR_ARG;
     Engine& e = h->e;
+    NvtxRange nvtx_range("di_upload_matrix");
     if (!norm || n_cells <= 0 || n_genes <= 0) return fail(e, DI_ERR_ARG, "di_upload_matrix: bad arguments");
     DI_CUDA(cudaSetDevice(e.cfg.device));
     int rc = ensure_matrix(e, n_cells, n_genes);
@@ -369,6 +379,7 @@ int di_upload_matrix(di_handle* h, const float* norm, int64_t n_cells, int64_t n
 int di_upload_counts(di_handle* h, const void* raw, int32_t dtype, int64_t n_cells, int64_t n_genes) {
     if (!h) return DI_ERR_ARG;
     Engine& e = h->e;
+    NvtxRange nvtx_range("di_upload_counts");
     if (!raw || n_cells <= 0 || n_genes <= 0 || (dtype != DI_DTYPE_F32 && dtype != DI_DTYPE_F64))
         return fail(e, DI_ERR_ARG, "di_upload_counts: bad arguments");
     DI_CUDA(cudaSetDevice(e.cfg.device));
@@ -432,6 +443,7 @@ int di_set_partition(di_handle* h, const int32_t* pred_idx, const int64_t* pred_
 int di_set_split(di_handle* h, const int32_t* train_rows, int64_t n_train, const int32_t* test_rows, int64_t n_test) {
     if (!h) return DI_ERR_ARG;
     Engine& e = h->e;
+    NvtxRange nvtx_range("di_set_split");
     if (!e.have_partition) return fail(e, DI_ERR_ARG, "di_set_split: call di_set_partition first");
     if (n_train < 0 || n_test < 0 || (n_train && !train_rows) || (n_test && !test_rows))
         return fail(e, DI_ERR_ARG, "di_set_split: bad arguments");
@@ -531,6 +543,7 @@ int di_get_adam_state(di_handle* h, int32_t s, float* mW1, float* vW1, float* mb
 int di_train_step(di_handle* h, const int32_t* rows, int32_t nrows, int64_t step, float* loss_out) {
     if (!h) return DI_ERR_ARG;
     Engine& e = h->e;
+    NvtxRange nvtx_range("di_train_step");
     if (!e.have_partition) return fail(e, DI_ERR_ARG, "di_train_step: no data (di_upload_matrix + di_set_partition)");
     if (!rows || nrows <= 0 || nrows > e.B || step < 0) return fail(e, DI_ERR_ARG, "di_train_step: need 1..B rows");
     for (int i = 0; i < nrows; ++i) if (rows[i] < 0 || rows[i] >= e.N) return fail(e, DI_ERR_ARG, "di_train_step: row out of range");
@@ -565,6 +578,7 @@ int di_validation_loss(di_handle* h, float* val_loss_out) {
 int di_train_epoch(di_handle* h, const int32_t* perm, int64_t first_step, float* loss_out, float* val_loss_out) {
     if (!h) return DI_ERR_ARG;
     Engine& e = h->e;
+    NvtxRange nvtx_range("di_train_epoch");
     if (!e.Xtr || e.n_train <= 0 || e.split_stale) return fail(e, DI_ERR_ARG, "di_train_epoch: call di_set_split first");
     if (!perm || first_step < 0) return fail(e, DI_ERR_ARG, "di_train_epoch: bad arguments");
     for (int64_t i = 0; i < e.n_train; ++i) if (perm[i] < 0 || perm[i] >= e.n_train) return fail(e, DI_ERR_ARG, "di_train_epoch: perm out of range");
@@ -606,6 +620,7 @@ int di_train_epoch(di_handle* h, const int32_t* perm, int64_t first_step, float*
 
 static int predict_impl(di_handle* h, const int32_t* rows, int64_t n, float* host_out, float* d_out, int64_t ld_out) {
     Engine& e = h->e;
+    NvtxRange nvtx_range("di_predict");
     if (!e.have_partition) return fail(e, DI_ERR_ARG, "di_predict: no data (di_upload_matrix + di_set_partition)");
     if (n < 0 || (!rows && n > e.N)) return fail(e, DI_ERR_ARG, "di_predict: bad row count");
     if (n == 0) return DI_OK;
@@ -683,6 +698,7 @@ int di_impute(di_handle* h, int32_t policy, const int32_t* slot_gene, int64_t n_
               int64_t ld_pred, int32_t out_dtype, void* out) {
     if (!h) return DI_ERR_ARG;
     Engine& e = h->e;
+    NvtxRange nvtx_range("di_impute");
     if (!e.d_raw) return fail(e, DI_ERR_ARG, "di_impute: no counts on the device (di_upload_counts)");
     if (!out || (out_dtype != DI_DTYPE_F32 && out_dtype != DI_DTYPE_F64) ||
         (policy != DI_POLICY_NONE && policy != DI_POLICY_RESTORE && policy != DI_POLICY_MAX))

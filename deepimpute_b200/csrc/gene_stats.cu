@@ -12,6 +12,8 @@
 
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/deepimpute_b200.h"
 
 namespace {
@@ -67,6 +69,7 @@ const char* di_gene_stats_last_error(void) { return g_err.c_str(); }
 
 int di_gene_stats(int32_t device, const void* raw, int32_t dtype, int64_t n_cells, int64_t n_genes, double* mean_out,
                   double* var_out, float* device_ms_out) {
+    struct R { R() { nvtxRangePushA("di_gene_stats"); } ~R() { nvtxRangePop(); } } nvtx_range;
     if (!raw || !mean_out || !var_out || n_cells <= 1 || n_genes <= 0 || (dtype != DI_DTYPE_F32 && dtype != DI_DTYPE_F64)) {
         g_err = "di_gene_stats: bad arguments";
         return DI_ERR_ARG;

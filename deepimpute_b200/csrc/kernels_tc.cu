@@ -416,22 +416,24 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                     const uint32_t ta = tmem + (uint32_t)(p.ts_acol0 + ls * TS_COLS);
                     // short chains (see acc_sum16): a b -> accumulator kb % nacc, the small products -> their own one
                     const uint32_t d_hi = tmem + (uint32_t)((kb % p.nacc) * p.n_cols);
-                    const uint32_t d_lo = tmem + (uint32_t)(p.nacc * p.n_cols);
+                    const uint32_t d_lo = p.lo_acc ? tmem + (uint32_t)(p.nacc * p.n_cols) : d_hi;
+                    const uint32_t first_lo = p.lo_acc ? (kb ? 1u : 0u) : (kb >= p.nacc ? 1u : 0u);   // accumulate flag of the block's first MMA
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
-                        umma_tf32_ts(d_lo, ta + BLOCK_K + j * UMMA_K, stage_desc<false>(sb, j), idesc_ts, (kb | j) ? 1u : 0u);
+                        umma_tf32_ts(d_lo, ta + BLOCK_K + j * UMMA_K, stage_desc<false>(sb, j), idesc_ts, j ? 1u : first_lo);
                         umma_tf32_ts(d_lo, ta + j * UMMA_K, stage_desc<false>(sb_lo, j), idesc_ts, 1u);
-                        umma_tf32_ts(d_hi, ta + j * UMMA_K, stage_desc<false>(sb, j), idesc_ts, (kb >= p.nacc || j) ? 1u : 0u);
+                        umma_tf32_ts(d_hi, ta + j * UMMA_K, stage_desc<false>(sb, j), idesc_ts, (!p.lo_acc || kb >= p.nacc || j) ? 1u : 0u);
                     }
                 } else if constexpr (X3) {
                     const uint32_t sa_lo = smem_u32(lo_base + (size_t)ls * stage_bytes), sb_lo = sa_lo + A_STAGE_BYTES;
                     const uint32_t d_hi = tmem + (uint32_t)((kb % p.nacc) * p.n_cols);
-                    const uint32_t d_lo = tmem + (uint32_t)(p.nacc * p.n_cols);
+                    const uint32_t d_lo = p.lo_acc ? tmem + (uint32_t)(p.nacc * p.n_cols) : d_hi;
+                    const uint32_t first_lo = p.lo_acc ? (kb ? 1u : 0u) : (kb >= p.nacc ? 1u : 0u);   // accumulate flag of the block's first MMA
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
-                        umma_tf32(d_lo, stage_desc<A_MN>(sa_lo, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                        umma_tf32(d_lo, stage_desc<A_MN>(sa_lo, j), stage_desc<false>(sb, j), idesc, j ? 1u : first_lo);
                         umma_tf32(d_lo, stage_desc<A_MN>(sa, j), stage_desc<false>(sb_lo, j), idesc, 1u);
-                        umma_tf32(d_hi, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, (kb >= p.nacc || j) ? 1u : 0u);
+                        umma_tf32(d_hi, stage_desc<A_MN>(sa, j), stage_desc<false>(sb, j), idesc, (!p.lo_acc || kb >= p.nacc || j) ? 1u : 0u);
                     }
                 } else {
 #pragma unroll
@@ -1154,8 +1156,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
                 // X3: round 1 (dout_hi in_hi) accumulates in columns [0, n_cols), rounds 0 and 2 (the small products) in
                 // [n_cols, 2 n_cols): short chains, see acc_sum16
                 const int round = pi / ppr;
-                const uint32_t dst = (X3 && round != 1) ? tmem + (uint32_t)p.n_cols : tmem;
-                const bool fresh = (pi % ppr) == 0 && (!X3 || round < 2);       // first pass of this accumulator
+                const uint32_t dst = (X3 && p.lo_acc && round != 1) ? tmem + (uint32_t)p.n_cols : tmem;
+                const bool fresh = (pi % ppr) == 0 && (round == 0 || (X3 && p.lo_acc && round == 1));   // first pass of this accumulator
                 for (int k = 0; k < cnt; ++k) {
                     const uint32_t sa = smem_u32(sA + (size_t)k * A_STAGE_BYTES);
                     const uint32_t sb = smem_u32(sB + (size_t)k * b_block_bytes);
@@ -1184,7 +1186,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_adam_kernel(const __grid_const
             float g[AD_R];
             __syncwarp();
             tmem_ld8(taddr + c * AD_R, g);
-            if constexpr (X3) {
+            if (X3 && p.lo_acc) {
                 float gl[AD_R];
                 tmem_ld8(taddr + p.n_cols + c * AD_R, gl);
 #pragma unroll
@@ -1421,12 +1423,12 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
             };
             // X3: the hi hi product and the two small products accumulate separately (columns [0, 128) and [128, 256),
             // see acc_sum16); the epilogue adds the two tiles
-            const uint32_t d_lo = tmem + (uint32_t)ADAM_TILE;
+            const uint32_t d_lo = p.lo_acc ? tmem + (uint32_t)ADAM_TILE : tmem;
             mbar_wait(&ops_bar[0], 0, 6);
             tc_fence_after();
             if constexpr (X3) {
                 mma_round(d_lo, set0, set1, true);                     // dout_hi in_lo
-                mma_round(tmem, set0, set2, true);                     // dout_hi in_hi
+                mma_round(tmem, set0, set2, p.lo_acc != 0);            // dout_hi in_hi
                 mbar_wait(&ops_bar[1], 0, 6);
                 tc_fence_after();
                 mma_round(d_lo, set3, set2, false);                    // dout_lo in_hi
@@ -1456,7 +1458,7 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
             float g[AD_R];
             __syncwarp();
             tmem_ld8(taddr + c * AD_R, g);
-            if constexpr (X3) {
+            if (X3 && p.lo_acc) {
                 float gl[AD_R];
                 tmem_ld8(taddr + ADAM_TILE + c * AD_R, gl);
 #pragma unroll
@@ -1927,6 +1929,19 @@ bool tc_rebind(Engine& e) {
 
 namespace {
 
+// Accumulator plan of one compensated GEMM (see acc_sum16): the cheapest layout whose longest accumulation chain stays
+// at or below MAX_CHAIN MMAs.  nkb = K blocks one CTA walks (four a b MMAs and eight small-product MMAs per block);
+// budget = tensor-memory columns the kernel may use.  Measured (profiles/r02e_accumulation.md): chains of 192-204 MMAs
+// leave a 1e-3 tail in the trained model, chains up to 96 do not.
+constexpr int MAX_CHAIN = 64;
+void plan_accumulators(int nkb, int n_cols, int budget, int* nacc, int* lo_acc) {
+    *nacc = 1; *lo_acc = 0;
+    if (nkb * 12 <= MAX_CHAIN || 2 * n_cols > budget) return;                 // one short chain (or no room for a second tile)
+    *lo_acc = 1;
+    const int want = (nkb * 4 + MAX_CHAIN - 1) / MAX_CHAIN;
+    *nacc = std::max(1, std::min(std::min(4, want), budget / n_cols - 1));
+}
+
 // Where and how one optimiser step of one sub-network group is launched.
 struct StepPlan {
     int s0 = 0, ns = 0;                         // sub-networks [s0, s0 + ns)
@@ -1967,14 +1982,16 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     const CUtensorMap& Yaux = which_x == 0 ? st->Ytr_aux : st->Ystep_aux;
     TcParams p = base_params(e);
     p.n_cols = e.Bp; p.tmem_cols = pow2_cols(e.Bp);
-    if (st->x3) {
-        // short accumulation chains (acc_sum16): up to four a b accumulators + one for the small products; kernels that
-        // may share an SM (pl.deep == 0: two CTAs per SM) stay within half of the 512 columns
-        const int budget = (st->lt || pl.deep != 0) ? 512 : 256;
-        p.lo_acc = 2 * e.Bp <= budget ? 1 : 0;
-        p.nacc = std::max(1, std::min(4, budget / e.Bp - p.lo_acc));
-        p.tmem_cols = pow2_cols((p.nacc + p.lo_acc) * e.Bp);
-    }
+    // short accumulation chains (acc_sum16), planned per kernel below; kernels that may share an SM (pl.deep == 0: two
+    // CTAs per SM) stay within half of the 512 tensor-memory columns
+    const int acc_budget = (st->lt || pl.deep != 0) ? 512 : 256;
+    int max_pp = 0;
+    for (int s = pl.s0; s < pl.s0 + pl.ns; ++s) max_pp = std::max(max_pp, e.Pp[s]);
+    auto plan = [&](TcParams& q, int nkb, int budget) {
+        if (!st->x3) return;
+        plan_accumulators(nkb, e.Bp, budget, &q.nacc, &q.lo_acc);
+        q.tmem_cols = pow2_cols((q.nacc + q.lo_acc) * e.Bp);
+    };
     p.row0 = a.row0; p.rows_per_block_y = 0;
     p.Y = a.Y; p.ldy = a.ldy; p.Hact = e.Hact; p.ldh = (int64_t)e.S * e.Hp; p.DZ2 = e.DZ2; p.DZ1 = e.DZ1;
     p.Hlo = e.Hlo; p.DZ2lo = e.DZ2lo; p.DZ1lo = e.DZ1lo;          // null unless DI_MATH_TF32X3
@@ -2000,32 +2017,37 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
         { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh; q.Hlo = e.Hlo - a.row0 * q.ldh;
           q.stages = cn.stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace;
           q.kpart = st->kpart[0]; q.kcount = st->kcount[0];
+          plan(q, cdiv(max_pp / BLOCK_K, st->lt_ks), 512);
           m.A = st->W1_mn; m.Alo = st->W1lo_mn; m.B = Xk; m.Blo = which_x == 0 ? st->Xtr_lo_k : st->Xstep_lo_k; m.C = Xk;
           launch_lt<TC_FWD1>(e, pl, "fwd1", m, q, dim3(st->lt_ks, mh, pl.ns), cn.smem); }
         { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
           q.stages = ca.stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 256;
           if (ca.aux) { q.aux_cols = st->aux_y; q.aux_row0 = a.row0; }
+          plan(q, e.Hp / BLOCK_K, 512);
           m.A = st->W2_mn; m.Alo = st->W2lo_mn; m.B = st->H_k; m.Blo = st->Hlo_k; m.C = Yaux;
           launch_lt<TC_FWD2>(e, pl, "fwd2", m, q, dim3(1, mo, pl.ns), ca.smem); }
         { TcParams q = p; q.m_tiles = mh; q.row0 = 0;
           q.stages = ca.stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 512;
           if (ca.aux) { q.aux_cols = st->aux_h; q.aux_row0 = 0; }
           q.kpart = st->kpart[1]; q.kcount = st->kcount[1];
+          plan(q, cdiv(e.Op / BLOCK_K, st->lt_ks), 512);
           m.A = st->W2_k; m.Alo = st->W2lo_k; m.B = st->DZ2_k; m.Blo = st->DZ2lo_k; m.C = st->H_aux;
           launch_lt<TC_BWD>(e, pl, "bwd", m, q, dim3(st->lt_ks, mh, pl.ns), ca.smem); }
     } else {
     { TcParams q = p; q.m_tiles = mh; q.Hact = e.Hact - a.row0 * q.ldh;   // kernel indexes h by row0 + b; training h starts at 0
       q.stages = c1.stages; q.lo_stages = c1.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace;
+      plan(q, max_pp / BLOCK_K, st->ts ? st->ts_acol0 : acc_budget);
       if (st->ts) {
-          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.nacc = st->nacc_ts; q.lo_acc = 1; q.ts_wbox = st->wbox1;
+          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.ts_wbox = st->wbox1;
           launch_on<TC_FWD1, true, true>(e, pl, "fwd1", st->W1_ts, Xk, Xk, q, dim3(1, mh, pl.ns), st->ts_smem1);
       } else if (st->x3) launch_on<TC_FWD1, true>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem);
       else launch_on<TC_FWD1, false>(e, pl, "fwd1", st->W1_mn, Xk, Xk, q, dim3(1, mh, pl.ns), c1.smem); }
     { TcParams q = p; q.m_tiles = mo; q.row0 = 0; q.Y = a.Y + a.row0 * a.ldy;
       q.stages = c2.stages; q.lo_stages = c2.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 256;
       if (c2.aux) { q.aux_cols = st->aux_y; q.aux_row0 = a.row0; }
+      plan(q, e.Hp / BLOCK_K, st->ts ? st->ts_acol0 : acc_budget);
       if (st->ts) {
-          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.nacc = st->nacc_ts; q.lo_acc = 1; q.ts_wbox = st->wbox2;
+          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.ts_wbox = st->wbox2;
           q.aux_cols = st->aux_y; q.aux_row0 = a.row0;
           launch_on<TC_FWD2, true, true>(e, pl, "fwd2", st->W2_ts, st->H_k, Yaux, q, dim3(1, mo, pl.ns), st->ts_smem2);
       } else if (st->x3) launch_on<TC_FWD2, true>(e, pl, "fwd2", st->W2_mn, st->H_k, Yaux, q, dim3(1, mo, pl.ns), c2.smem);
@@ -2033,8 +2055,9 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     { TcParams q = p; q.m_tiles = mh; q.row0 = 0;
       if (c3.aux) { q.aux_cols = st->aux_h; q.aux_row0 = 0; }
       q.stages = c3.stages; q.lo_stages = c3.lo_stages; if (!pl.graph && st->d_trace) q.trace = st->d_trace + 512;
+      plan(q, e.Op / BLOCK_K, st->ts_bwd ? st->ts_acol0 : acc_budget);
       if (st->ts_bwd) {
-          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.nacc = st->nacc_ts; q.lo_acc = 1; q.ts_wbox = TILE_M;
+          q.stages = st->ts_stages; q.lo_stages = st->ts_lo; q.tmem_cols = st->ts_tmem; q.ts_acol0 = st->ts_acol0; q.ts_wbox = TILE_M;
           q.aux_cols = st->aux_h; q.aux_row0 = 0;
           launch_on<TC_BWD, true, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), st->ts_smem2);
       } else if (st->x3) launch_on<TC_BWD, true>(e, pl, "bwd", st->W2_k, st->DZ2_k, st->H_aux, q, dim3(1, mh, pl.ns), c3.smem);
@@ -2042,7 +2065,9 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     }
     if (st->simt_adam && !pl.graph) { simt_adam_only(e, a); return; }
     TcParams q = p;
-    q.n_cols = ADAM_TILE; q.tmem_cols = st->x3 ? 2 * ADAM_TILE : ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;   // X3: a b and the small products apart
+    q.n_cols = ADAM_TILE; q.tmem_cols = ADAM_TILE; q.nkb_adam = e.Bp / BLOCK_K;
+    q.nacc = 1; q.lo_acc = 0;
+    if (st->x3 && (e.Bp / BLOCK_K) * 12 > MAX_CHAIN) { q.lo_acc = 1; q.tmem_cols = 2 * ADAM_TILE; }   // long batch: a b and the small products apart
     q.row0 = a.row0; q.wbox = st->wbox1; q.wbox2 = st->wbox2;
     q.W1 = e.W1; q.mW1 = e.mW1; q.vW1 = e.vW1; q.W2 = e.W2; q.mW2 = e.mW2; q.vW2 = e.vW2;
     q.W1lo = st->lt ? e.W1lo : nullptr; q.W2lo = st->lt ? e.W2lo : nullptr;
@@ -2223,10 +2248,9 @@ void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_va
     const CUtensorMap& Xk = which_x == 2 ? st->Xte_k : st->Xchunk_k;
     TcParams p = base_params(e);
     p.n_cols = e.infer_tile; p.tmem_cols = e.infer_tile; p.stages = st->infer.stages; p.lo_stages = st->infer.lo_stages;
-    if (st->x3) {        // accumulators as in training (one CTA per SM: all 512 columns)
-        p.lo_acc = 1;
-        p.nacc = std::max(1, std::min(4, 512 / e.infer_tile - 1));
-        p.tmem_cols = pow2_cols((p.nacc + 1) * e.infer_tile);
+    if (st->x3) {        // accumulators as in training (one CTA per SM: all 512 columns); longest K loop: FWD1
+        plan_accumulators(e.maxPp / BLOCK_K, e.infer_tile, 512, &p.nacc, &p.lo_acc);
+        p.tmem_cols = pow2_cols((p.nacc + p.lo_acc) * e.infer_tile);
     }
     p.rows_per_block_y = e.infer_tile;
     p.ldh = (int64_t)e.S * e.Hp;
