@@ -351,7 +351,7 @@ def oracle_check(eng, wl, pred_idx, targ_idx, mine, n_train, steps_cap=None):
     rel = lambda a, b: float(np.max(np.abs(np.asarray(a, np.float64) - b)) / (np.max(np.abs(b)) + 1e-300))   # noqa: E731
     max_rel_w = max(rel(a, b) for a, b in zip(got_w, ref.get_weights()[0]))
     max_rel = rel(got, want)
-    tol = 2e-3
+    tol = 1e-3            # the north star's bound; measured 1e-6 .. 5e-5 (profiles/r02e_accumulation.md)
     return {"what": "sub-network {} of the timed engine after one epoch ({} Adam steps) from its initial weights vs the "
                     "CPU oracle trained alone on the same rows".format(gid, -(-n_train // wl["B"])),
             "max_rel": max_rel, "max_rel_weights": max_rel_w, "tol": tol, "ok": bool(max_rel < tol and max_rel_w < tol),

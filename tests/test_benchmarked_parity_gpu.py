@@ -15,8 +15,10 @@ model.  The tests therefore
   4. check the independence claim itself on the device: an engine that holds only the sampled sub-networks gives
      bit-identical predictions to the full model's columns, and its loss / val_loss equal the oracle's.
 
-Tolerances (error against the scale of the compared tensor, as in test_engine_gpu.py): predictions 2e-3, weights 2e-3,
-losses 1e-3 relative -- the ``tf32x3`` row of DESIGN.md section 4.
+Tolerances (error against the scale of the compared tensor, as in test_engine_gpu.py): predictions 2e-4, weights 5e-4,
+losses 1e-4 relative -- the ``tf32x3`` row of DESIGN.md section 4.  Measured on a B200 with short accumulation chains
+(kernels_tc.cu, ``acc_sum16``): predictions 1e-6 .. 2e-6, weights 3e-6 .. 5e-5; with one long chain per tile the same
+checks sat at 2e-3 .. 4e-3 (profiles/r02e_accumulation.md), which is what these bounds would catch.
 """
 import numpy as np
 import pytest
@@ -94,12 +96,12 @@ def _check_sampled(monkeypatch, name, sampled, epochs):
     del Xtr, Ytr
 
     # (3) compare
-    np.testing.assert_allclose(np.asarray(part_hist), np.asarray(ref_hist), rtol=1e-3)
+    np.testing.assert_allclose(np.asarray(part_hist), np.asarray(ref_hist), rtol=1e-4)
     want = np.hstack(ref.forward(stage(norm, sel_pred, sel_targ, rows)[0]))
-    assert rel_err(part_pred, want) < 2e-3
+    assert rel_err(part_pred, want) < 2e-4
     for k, s in enumerate(sampled):
         for got_a, ref_a in zip(full_w[s], ref.get_weights()[k]):
-            assert rel_err(got_a, ref_a) < 2e-3
+            assert rel_err(got_a, ref_a) < 5e-4
     # the full model's own losses are finite, fall, and contain the sampled part
     fh = np.asarray(full_hist)
     assert np.isfinite(fh).all() and (fh[:, 0] > np.asarray(part_hist)[:, 0]).all()
@@ -153,11 +155,11 @@ def test_kernel_families_follow_the_oracle(monkeypatch, knobs):
         p = epoch_permutation(SEED, epoch, len(tr))
         got = eng.train_epoch(p)
         loss, step = ref.train_epoch(Xtr, Ytr, p, step)
-        np.testing.assert_allclose(got, (loss, ref.loss(Xte, Yte)), rtol=1e-3)
+        np.testing.assert_allclose(got, (loss, ref.loss(Xte, Yte)), rtol=1e-4)
     assert eng.graph_fallbacks() == 0
     want = np.hstack(ref.forward(stage(norm, pred_idx, targ, np.arange(N))[0]))
-    assert rel_err(eng.predict(), want) < 2e-3
+    assert rel_err(eng.predict(), want) < 1e-4          # measured 1e-6; a single long chain per tile gives 2.8e-3 here
     for got_w, ref_w in zip(eng.get_weights(), ref.get_weights()):
         for a, b in zip(got_w, ref_w):
-            assert rel_err(a, b) < 2e-3
+            assert rel_err(a, b) < 5e-4                 # measured 3e-5
     eng.close()
