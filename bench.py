@@ -364,7 +364,8 @@ def sharding_check(ctx, rank, world, local):
     import torch
     from deepimpute_b200 import parallel
     from deepimpute_b200.engine import Engine, epoch_permutation
-    S, O, H, B, N, G = 2 * world + 1, 64, 48, 32, 700, 900
+    S, O, H, B, N = 2 * world + 1, 64, 48, 32, 700
+    G = S * O + 260                              # disjoint targets for every sub-network plus spare genes
     rng = np.random.default_rng(3)
     lam = rng.gamma(0.6, 3.0, size=(1, G)) * rng.gamma(2.0, 0.5, size=(N, 1))
     norm = np.log1p(rng.poisson(lam)).astype(np.float32)
@@ -622,7 +623,10 @@ def main():
     checks = {}
     if not args.no_checks:
         if world > 1:
-            checks["sharding_check"] = sharding_check(ctx, rank, world, local)
+            try:
+                checks["sharding_check"] = sharding_check(ctx, rank, world, local)
+            except Exception as exc:                                    # report, never lose the bench line (every rank fails alike)
+                checks["sharding_check"] = {"ok": False, "error": repr(exc)}
         elif wl["name"] != "c5" or os.environ.get("DI_BENCH_ORACLE_C5") == "1":
             # one oracle epoch of one sub-network: ~5 s at c3 (batch 64); ~1 min at c5 (batch 256), on request only
             try:
