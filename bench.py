@@ -358,6 +358,51 @@ def oracle_check(eng, wl, pred_idx, targ_idx, mine, n_train, steps_cap=None):
             "oracle_seconds": round(secs, 1)}
 
 
+def multinet_shard_check(ctx, rank, world, local):
+    """``--gpus N``: the reference-facing object itself, sharded.  ``MultiNet(shard=ctx).fit(df).predict(df)`` on every
+    rank (sub-networks split over the ranks, NCCL all-reduce of the epoch losses, NCCL all-gather of the prediction
+    blocks, fused imputation tail on every rank) must return the imputed frame of the unsharded ``MultiNet`` bit for bit."""
+    import contextlib
+    import pandas as pd
+    from deepimpute_b200 import MultiNet
+    rng = np.random.default_rng(5)
+    n_cells, n_genes, rank_k = 640, 2400, 8
+    lam = (rng.gamma(2.0, 0.5, size=(n_cells, rank_k)) @ rng.gamma(0.3, 1.0, size=(n_genes, rank_k)).T) * \
+        rng.lognormal(0.0, 1.0, size=n_genes) * (4.0 / rank_k)
+    counts = rng.poisson(lam).astype(np.float64)
+    counts[0, 0] = max(counts[0, 0], 12.0)
+    frame = pd.DataFrame(counts, index=["c{}".format(i) for i in range(n_cells)], columns=["g{}".format(j) for j in range(n_genes)])
+    kw = dict(seed=1234, ncores=1, max_epochs=3, patience=100, verbose=0, sub_outputdim=128,
+              architecture=[{"type": "dense", "neurons": 64, "activation": "relu"}, {"type": "dropout", "rate": 0.2}])
+    with contextlib.redirect_stdout(sys.stderr):
+        net = MultiNet(shard=ctx, device=local, **kw)
+        net.fit(frame, NN_lim=2048)
+        out = net.predict(frame)
+    ctx.barrier()
+    result = None
+    if rank == 0:
+        try:                                     # rank 0 works alone here: whatever happens, it must reach the barrier below
+            with contextlib.redirect_stdout(sys.stderr):
+                one = MultiNet(device=local, **kw)
+                one.fit(frame, NN_lim=2048)
+                ref = one.predict(frame)
+            loss_rel = float(np.max(np.abs(np.asarray(net.history["loss"]) - np.asarray(one.history["loss"])) /
+                                    np.abs(np.asarray(one.history["loss"]))))
+            diff = float(np.max(np.abs(out.values - ref.values)))
+            result = {"what": "MultiNet(shard=ctx).fit/predict, {} sub-networks over {} ranks, vs the unsharded MultiNet"
+                              .format(len(net.predictors), world),
+                      "max_abs_diff_imputed": diff, "max_rel_diff_losses": loss_rel,
+                      "ok": bool(diff == 0.0 and loss_rel < 1e-5)}
+            if one.engine is not None:
+                one.engine.close()
+        except Exception as exc:
+            result = {"ok": False, "error": repr(exc)}
+    if net.engine is not None:
+        net.engine.close()
+    ctx.barrier()
+    return result
+
+
 def sharding_check(ctx, rank, world, local):
     """``--gpus N``: a small model sharded over the N ranks must give the prediction blocks of the unsharded model
     bit for bit (global sub-network numbers key the initial weights and the dropout stream).  Rank 0 trains both."""
@@ -395,7 +440,7 @@ def sharding_check(ctx, rank, world, local):
     torch.distributed.all_reduce(l)
     if rank != 0:
         return None
-    full_losses, full = run(list(range(S)))
+    full_losses, full = run(list(range(S)))          # (no collective follows: rank 0 may take its time, or fail, alone)
     allb = allb.cpu().numpy().reshape(world, N, width)
     diff = 0.0
     for r, ids in enumerate(owned):
@@ -623,10 +668,11 @@ def main():
     checks = {}
     if not args.no_checks:
         if world > 1:
-            try:
-                checks["sharding_check"] = sharding_check(ctx, rank, world, local)
-            except Exception as exc:                                    # report, never lose the bench line (every rank fails alike)
-                checks["sharding_check"] = {"ok": False, "error": repr(exc)}
+            for name, fn in (("sharding_check", sharding_check), ("multinet_shard_check", multinet_shard_check)):
+                try:
+                    checks[name] = fn(ctx, rank, world, local)
+                except Exception as exc:                                # report, never lose the bench line (every rank fails alike)
+                    checks[name] = {"ok": False, "error": repr(exc)}
         elif wl["name"] != "c5" or os.environ.get("DI_BENCH_ORACLE_C5") == "1":
             # one oracle epoch of one sub-network: ~5 s at c3 (batch 64); ~1 min at c5 (batch 256), on request only
             try:
