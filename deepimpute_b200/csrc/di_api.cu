@@ -270,7 +270,8 @@ int di_create(di_handle** out, const di_config* cfg, const int32_t* n_pred) {
         int64_t cr = (int64_t)(1536ll << 20) / std::max<int64_t>(per_row, 1);
         // inference tile: 256 cells per CTA on the tensor-core path (N = 256 MMAs read 12 KB of operands per 128 cycles
         // instead of 8 KB per 64: measured 5.09 -> 4.50 ms for 16k cells x 40 sub-networks), 128 otherwise
-        e.infer_tile = cfg->math_mode != DI_MATH_FP32 ? 256 : 128;
+        // (tf32x3: the persistent inference kernel works on 128-cell tiles with a double-buffered accumulator)
+        e.infer_tile = cfg->math_mode == DI_MATH_TF32 ? 256 : 128;
         if (const char* v = getenv("DEEPIMPUTE_B200_INFER_TILE")) if (atoi(v) == 128) e.infer_tile = 128;
         cr = std::max<int64_t>(e.infer_tile, std::min<int64_t>(cr / e.infer_tile * e.infer_tile, 16384));
         e.chunk_rows = cr;

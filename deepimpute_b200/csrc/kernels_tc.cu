@@ -59,6 +59,9 @@ struct TcParams {
     int S, H, O, Hp, Op;
     int n_cols;                 // UMMA N: batch rows (FWD*/BWD) or input-feature tile width (ADAM)
     int tmem_cols;              // power of two >= (nacc + lo_acc) * n_cols
+    int row_tiles;              // persistent inference kernel: 128-cell tiles per sub-network and feature tile
+    int conv_teams;             // converter-warp kernels: 1 = all eight converter warps share every slab, 2 = two teams of four
+                                // warps take alternate slabs (the conversion of one slab is a latency chain, not a throughput limit)
     int nacc;                   // X3: accumulators the a b products of successive K blocks rotate through (>= 1) ...
     int lo_acc;                 // ... and 1 if the small products a_lo b + a b_lo have an accumulator of their own (see acc_sum)
     int stages;                 // ring of raw (hi) slabs written by TMA
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < lo_stages; ++i) { mbar_init(&lo_ready[i], NCONV); mbar_init(&lo_free[i], 1); }
+        for (int i = 0; i < lo_stages; ++i) { mbar_init(&lo_ready[i], NCONV / p.conv_teams); mbar_init(&lo_free[i], 1); }
         mbar_init(&tmem_full_bar, 1);
         mbar_init(&aux_bar, 1);
         fence_barrier_init();
@@ -278,9 +281,12 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
 
     // residual pass (X3): lo = a - trunc19(a) for every float of the slab TMA just delivered, written to the next slab
     // of the residual ring (element-wise: the swizzled layout carries over unchanged).  Run by 8 warps (0-3, 6-9).
-    auto convert = [&](int cid) {
-        const int per_thread = (int)(hi_bytes / 16) / NCONV;          // float4 per thread; hi_bytes is a multiple of 4 KB
-        for (int kb = 0; kb < nkb; ++kb) {
+    auto convert = [&](int cid_all) {
+        // two teams (warps 0-3, warps 6-9): team t converts slabs t, t + 2, ...; one team: everybody converts every slab
+        const int teams = p.conv_teams, CT = NCONV / teams;           // threads per slab
+        const int team = teams == 2 ? (cid_all >> 7) : 0, cid = teams == 2 ? (cid_all & 127) : cid_all;
+        const int per_thread = (int)(hi_bytes / 16) / CT;             // float4 per thread; hi_bytes is a multiple of 4 KB
+        for (int kb = team; kb < nkb; kb += teams) {
             const int lstages = X3 ? lo_stages : 1;       // (plain TF32 never instantiates a call of this lambda)
             const int st = kb % stages, ls = kb % lstages;
             mbar_wait(&full_bar[st], (kb / stages) & 1, 1);
@@ -288,7 +294,9 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
             if constexpr (TS) {
                 // weights: this thread owns feature `quad * 32 + lane` (the TMEM lane its warp may write) and half of the
                 // slab's 32 k; W and its residual go to tensor memory, columns [ls * 64, +32) and [ls * 64 + 32, +32)
-                const int hw = (int)(threadIdx.x >> 5), quad = hw & 3, half = hw >= 6 ? 1 : 0, ml = quad * 32 + (cid & 31);
+                const int hw = (int)(threadIdx.x >> 5), quad = hw & 3, ml = quad * 32 + (cid & 31);
+                const int h_first = teams == 2 ? 0 : (hw >= 6 ? 1 : 0), h_last = teams == 2 ? 1 : h_first;   // halves of the 32 k this thread converts
+                for (int half = h_first; half <= h_last; ++half) {
                 float hi[16], lo[16];
                 if constexpr (A_MN) {
                     // FWD1 / FWD2: plain [32 k][wbox features] tile; a warp reads 32 consecutive features of one k
@@ -315,10 +323,11 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                 const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.ts_acol0 + ls * TS_COLS + half * 16);
                 tmem_st16(ta, hi);
                 tmem_st16(ta + BLOCK_K, lo);
+                }
                 // activations: residual slab in shared memory, as in the SS path but for the B part only
                 const uint32_t bhi = smem_u32(smem + (size_t)st * stage_bytes + A_STAGE_BYTES) + cid * 16;
                 const uint32_t blo = smem_u32(lo_base + (size_t)ls * lo_stage_bytes) + cid * 16;
-                for (uint32_t off = 0; off + cid * 16 < b_stage_bytes; off += NCONV * 16) {
+                for (uint32_t off = 0; off + cid * 16 < b_stage_bytes; off += CT * 16) {
                     float4 v;
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(bhi + off));
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
@@ -340,12 +349,12 @@ __global__ void __launch_bounds__(X3 ? NTHREADS_X3 : NTHREADS, X3 ? 1 : 2) tc_ke
                 for (int u = 0; u < 4; ++u)
                     if (i0 + u < per_thread)
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(hi + (i0 + u) * (NCONV * 16)));
+                                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(hi + (i0 + u) * (CT * 16)));
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (i0 + u < per_thread)
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
-                                     ::"r"(lo + (i0 + u) * (NCONV * 16)), "f"(tf32_residual(v[u].x)), "f"(tf32_residual(v[u].y)),
+                                     ::"r"(lo + (i0 + u) * (CT * 16)), "f"(tf32_residual(v[u].x)), "f"(tf32_residual(v[u].y)),
                                        "f"(tf32_residual(v[u].z)), "f"(tf32_residual(v[u].w)) : "memory");
             }
             fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core
@@ -1017,6 +1026,188 @@ __global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_kernel(const __grid_const
     DI_TRACE_T0(5);
 }
 
+// ================================================================== inference: persistent, epilogue under the main loop
+// The two forward layers over all cells (model.predict, multinet.py:278-280, and the validation pass of every epoch).
+// One CTA per SM walks tiles t = blockIdx.x, + gridDim.x, ... of [128 features x 128 cells] (row tile fastest, then feature
+// tile, then sub-network).  Operands as in tc_lt_kernel: [W | W_lo | act | act_lo] slabs by TMA, twelve MMAs per K block.
+// Tensor memory holds TWO accumulator stages of two tiles each (a b products / the small products, 4 x 128 = 512 columns):
+// while the sixteen epilogue warps drain stage i & 1 (bias, relu or softplus, optional wMSE, stores), the MMA warp is
+// already filling the other stage with the next tile, and the TMA ring never drains between tiles.  In tc_lt_kernel (one
+// tile per CTA) the tensor pipe idles during prologue, first-slab latency and the whole epilogue: 44 % / 33 % active in
+// FWD1 / FWD2 (profiles/r02_full_infer_lt.md).
+constexpr int INF_TILE = 128;
+
+template <int OP>
+__global__ void __launch_bounds__(LT_THREADS, 1) tc_lt_infer_kernel(const __grid_constant__ LtMaps maps, const TcParams p) {
+    static_assert(OP == TC_FWD1 || OP == TC_FWD2, "inference runs the two forward layers");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr uint32_t b_bytes = INF_TILE * BLOCK_K * 4;
+    constexpr uint32_t stage_bytes = 2 * A_STAGE_BYTES + 2 * b_bytes;           // 64 KB
+    const int stages = p.stages;
+    __shared__ uint64_t full_bar[LT_MAX_STAGES], empty_bar[LT_MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ double red[2][LT_EPI_WARPS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], LT_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == LT_EPI_WARPS && lane == 0) {
+        prefetch_tensormap(&maps.A); prefetch_tensormap(&maps.Alo); prefetch_tensormap(&maps.B); prefetch_tensormap(&maps.Blo);
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, 512u);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    const int row_tiles = p.row_tiles, m_tiles = p.m_tiles;
+    const int n_tiles = p.S * m_tiles * row_tiles;
+    // tile t -> (sub-network, feature tile, row tile) and its operand coordinates
+    auto tile_of = [&](int t, int& s, int& m0, int& row_tile, int& nkb, int& a_c1, int& b_c0) {
+        row_tile = t % row_tiles;
+        const int mt = (t / row_tiles) % m_tiles;
+        s = t / (row_tiles * m_tiles) + p.s_base;
+        m0 = mt * TILE_M;
+        if constexpr (OP == TC_FWD1) { const SubnetDesc d = p.desc[s]; nkb = d.Pp / BLOCK_K; a_c1 = (int)d.coff; b_c0 = (int)d.coff; }
+        else { nkb = p.Hp / BLOCK_K; a_c1 = s * p.Hp; b_c0 = s * p.Hp; }
+    };
+
+    if (warp == LT_EPI_WARPS) {
+        // ===== TMA producer: the ring runs across tiles =====
+        if (elect_one()) {
+            int it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                int s, m0, row_tile, nkb, a_c1, b_c0;
+                tile_of(t, s, m0, row_tile, nkb, a_c1, b_c0);
+                const int b_c1 = (int)(p.row0 + (int64_t)row_tile * INF_TILE);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int st = it % stages;
+                    if (it >= stages) mbar_wait(&empty_bar[st], ((it / stages) - 1) & 1, 2);
+                    mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
+                    uint8_t* sa = smem + (size_t)st * stage_bytes;
+                    const int k = kb * BLOCK_K;
+                    load_stage<true>(sa, &maps.A, &full_bar[st], m0, a_c1 + k, TILE_M);
+                    load_stage<true>(sa + A_STAGE_BYTES, &maps.Alo, &full_bar[st], m0, a_c1 + k, TILE_M);
+                    tma_load_2d(sa + 2 * A_STAGE_BYTES, &maps.B, &full_bar[st], b_c0 + k, b_c1);
+                    tma_load_2d(sa + 2 * A_STAGE_BYTES + b_bytes, &maps.Blo, &full_bar[st], b_c0 + k, b_c1);
+                }
+            }
+        }
+    } else if (warp == LT_EPI_WARPS + 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            const uint32_t idesc = idesc_for(INF_TILE, true, false);
+            int it = 0, i = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+                int s, m0, row_tile, nkb, a_c1, b_c0;
+                tile_of(t, s, m0, row_tile, nkb, a_c1, b_c0);
+                const int acc = i & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((i >> 1) & 1) ^ 1, 12);     // the epilogue has drained this stage (passes at once the first time)
+                tc_fence_after();
+                const uint32_t d_hi = tmem + (uint32_t)(acc * 2 * INF_TILE), d_lo = d_hi + INF_TILE;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int st = it % stages;
+                    mbar_wait(&full_bar[st], (it / stages) & 1, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                    const uint32_t sa_lo = sa + A_STAGE_BYTES, sb = sa + 2 * A_STAGE_BYTES, sb_lo = sb + b_bytes;
+#pragma unroll
+                    for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
+                        umma_tf32(d_lo, stage_desc<true>(sa_lo, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                        umma_tf32(d_lo, stage_desc<true>(sa, j), stage_desc<false>(sb_lo, j), idesc, 1u);
+                        umma_tf32(d_hi, stage_desc<true>(sa, j), stage_desc<false>(sb, j), idesc, (kb | j) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[st]);
+                }
+                umma_commit(&tmem_full_bar[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue: warp -> TMEM lane quadrant (warp % 4), 32 of the 128 cell columns (warp / 4) =====
+        const int quad = warp & 3, cg = warp >> 2;
+        const int fl = quad * 32 + lane;
+        int i = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            int s, m0, row_tile, nkb, a_c1, b_c0;
+            tile_of(t, s, m0, row_tile, nkb, a_c1, b_c0);
+            const int acc = i & 1;
+            const int out_dim = (OP == TC_FWD1) ? p.Hp : p.Op;
+            const int f = m0 + fl;
+            const bool f_ok = f < out_dim;
+            const int64_t bias_i = (int64_t)s * out_dim + f;
+            const float bias = f_ok ? ((OP == TC_FWD1) ? p.b1[bias_i] : p.b2[bias_i]) : 0.f;
+            const int64_t row0 = p.row0 + (int64_t)row_tile * INF_TILE;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 2 * INF_TILE);
+            mbar_wait(&tmem_full_bar[acc], (i >> 1) & 1, 4);
+            tc_fence_after();
+            float part = 0.f;
+            const int rows_left = p.n_valid - row_tile * INF_TILE;
+#pragma unroll 1
+            for (int c = cg * 32; c < cg * 32 + 32; c += 16) {
+                float v[16];
+                __syncwarp();
+                acc_sum16(taddr, c, INF_TILE, 1, 1, true, v);
+                if (m0 >= out_dim || !f_ok) continue;
+                if constexpr (OP == TC_FWD1) {
+                    float* dst = p.Hact + (row0 + c) * p.ldh + (int64_t)s * p.Hp + f;
+                    float* dlo = p.Hlo + (row0 + c) * p.ldh + (int64_t)s * p.Hp + f;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float a = fmaxf(v[k] + bias, 0.f);
+                        dst[(int64_t)k * p.ldh] = a;
+                        dlo[(int64_t)k * p.ldh] = tf32_residual(a);
+                    }
+                } else {
+                    float yh[16], sg[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) softplus_sigmoid(v[k] + bias, yh[k], sg[k]);
+                    if (p.out && f < p.O) {
+                        float* dst = p.out + ((int64_t)row_tile * INF_TILE + c) * p.ld_out + (int64_t)s * p.O + f;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if (c + k < rows_left) dst[(int64_t)k * p.ld_out] = yh[k];
+                    }
+                    if (p.Y) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const float y = __ldg(p.Y + (row0 + c + k) * p.ldy + bias_i);
+                            const float diff = y - yh[k];
+                            part += y * diff * diff;
+                        }
+                    }
+                }
+            }
+            // this warp has read its part of the stage: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if constexpr (OP == TC_FWD2) {
+                if (p.loss) {
+                    double dpart = (double)part;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) dpart += __shfl_xor_sync(0xffffffffu, dpart, off);
+                    if (lane == 0) red[acc][warp] = dpart;
+                    named_bar_sync(1, LT_EPI_WARPS * 32);
+                    if (threadIdx.x == 0) {
+                        double tot = 0.0;
+#pragma unroll
+                        for (int w = 0; w < LT_EPI_WARPS; ++w) tot += red[acc][w];
+                        atomicAdd(p.loss, tot);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
 // ============================================================================================ ADAM (weight update)
 // One CTA: dW tile [128 output features (lanes)] x [n_cols input features (columns)] = dout^T in, K = padded batch.
 // shared memory: operands (all K blocks at once) | ring of AD_STAGES x {w, m, v} x [AD_R rows][wbox floats]
@@ -1510,6 +1701,8 @@ struct TcState {
     CUtensorMap W1lo_mn, W2lo_mn, W2lo_k, Hlo_k, DZ2lo_k, Xstep_lo_k, Xtr_lo_k, Xte_lo_k, Xchunk_lo_k, Hchunk_lo_k;
     struct LtCfg { int stages = 0, smem = 0; bool aux = false; };
     LtCfg lt_train, lt_train_noaux, lt_infer;
+    bool wlo_stale = true;                                 // converter family: W_lo is not kept by ADAM; inference refreshes it on demand
+    int inf_stages = 0, inf_smem = 0;                      // persistent inference kernel
     int lt_ks = 1;                                         // split-K factor of FWD1 / BWD (1: one CTA walks the whole K loop)
     int nacc_ts = 1;                                       // accumulators of the TS kernels (their weight slabs share tensor memory)
     float* kpart[2] = {nullptr, nullptr};                  // scratch tiles of FWD1 / BWD: [S][m_tiles][lt_ks][Bp][128]
@@ -1590,6 +1783,7 @@ TcParams base_params(Engine& e) {
     p.drop_thresh = r > 0.0 ? (uint32_t)(r * 4294967296.0) : 0u;
     p.keep_scale = 1.0f;
     p.nacc = 1; p.lo_acc = 0;
+    { static const int teams = [] { const char* v = getenv("DEEPIMPUTE_B200_CONV_TEAMS"); return (v && atoi(v) == 1) ? 1 : 2; }(); p.conv_teams = teams; }
     return p;
 }
 
@@ -1760,6 +1954,8 @@ bool tc_init(Engine& e) {
         st->lt_train_noaux = lt_cfg(e.Bp, 0);
         if (st->lt_train.stages < 3) st->lt_train = st->lt_train_noaux;
         st->lt_infer = lt_cfg(e.infer_tile, 0);
+        st->inf_stages = 3;                                  // persistent inference kernel: 3 x 64 KB slabs
+        st->inf_smem = st->inf_stages * (2 * (int)A_STAGE_BYTES + 2 * INF_TILE * BLOCK_K * 4) + 1024;
         if (st->lt_train.stages < 2 || st->lt_infer.stages < 2) st->lt = false;
         if (st->lt) {
             // split K of FWD1 / BWD: as many CTAs per tile as idle SMs allow (at most 4), never more than K blocks
@@ -1879,6 +2075,10 @@ bool tc_init(Engine& e) {
         set((const void*)tc_lt_kernel<TC_FWD2>, ml);
         set((const void*)tc_lt_kernel<TC_BWD>, ml);
     }
+    if (st->x3) {
+        set((const void*)tc_lt_infer_kernel<TC_FWD1>, st->inf_smem);
+        set((const void*)tc_lt_infer_kernel<TC_FWD2>, st->inf_smem);
+    }
     set((const void*)tc_adam_kernel<false>, st->smem_adam);
     set((const void*)tc_adam_kernel<true>, st->smem_adam);
     if (st->adam_big) {
@@ -1978,6 +2178,7 @@ struct WindowScope {    // training launches of an engine whose optimiser state 
 
 void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const StepPlan& pl) {
     WindowScope window(st);
+    st->wlo_stale = true;
     const CUtensorMap& Xk = which_x == 0 ? st->Xtr_k : st->Xstep_k;
     const CUtensorMap& Yaux = which_x == 0 ? st->Ytr_aux : st->Ystep_aux;
     TcParams p = base_params(e);
@@ -2204,6 +2405,7 @@ bool tc_train_epoch_graph(Engine& e, int64_t first_step, const float* lr_t, int6
     if (cudaMemcpyAsync(st->d_step_base, &base, sizeof base, cudaMemcpyHostToDevice, e.stream) != cudaSuccess) return false;
     if (cudaMemcpyAsync(st->d_lr_table, lr_t, (size_t)n_steps * sizeof(float), cudaMemcpyHostToDevice, e.stream) != cudaSuccess) return false;
     if (cudaGraphLaunch(st->epoch_exec, e.stream) != cudaSuccess) { cudaGetLastError(); return false; }
+    st->wlo_stale = true;
     e.launches += st->graph_nodes;
     return true;
 }
@@ -2217,6 +2419,7 @@ __global__ void residual_kernel(const float* __restrict__ w, float* __restrict__
 
 void tc_weights_changed(Engine& e, int s) {
     if (!e.W1lo || !e.W2lo) return;
+    // (this refreshes one sub-network; the others may be stale in the converter family: leave the flag alone)
     const int64_t n1 = (int64_t)e.Pp[s] * e.Hp, o1 = e.coff[s] * e.Hp, n2 = (int64_t)e.Hp * e.Op, o2 = (int64_t)s * e.Hp * e.Op;
     residual_kernel<<<(unsigned)std::min<int64_t>((n1 + 255) / 256, 1184), 256, 0, e.stream>>>(e.W1 + o1, e.W1lo + o1, n1);
     residual_kernel<<<(unsigned)std::min<int64_t>((n2 + 255) / 256, 1184), 256, 0, e.stream>>>(e.W2 + o2, e.W2lo + o2, n2);
@@ -2257,21 +2460,30 @@ void tc_forward(Engine& e, int which_x, int64_t row0, int64_t rows, int64_t n_va
     p.n_valid = (int)n_valid; p.training = 0; p.drop_thresh = 0;
     const int row_tiles = (int)(rows / e.infer_tile);
     const int mh = cdiv(e.Hp, TILE_M), mo = cdiv(e.Op, TILE_M);
-    if (st->lt) {
-        const TcState::LtCfg& c = st->lt_infer;
+    if (st->x3) {
+        // persistent kernel, every operand by TMA.  The converter family does not keep W_lo during training: bring it
+        // up to date first (one element-wise pass over the weights, 43 MB at c3)
+        if (!st->lt && st->wlo_stale) {
+            const int64_t n1 = e.PT * e.Hp, n2 = (int64_t)e.S * e.Hp * e.Op;
+            residual_kernel<<<1184, 256, 0, e.stream>>>(e.W1, e.W1lo, n1);
+            residual_kernel<<<1184, 256, 0, e.stream>>>(e.W2, e.W2lo, n2);
+            st->wlo_stale = false;
+        }
         LtMaps m;
-        p.stages = c.stages;
+        p.stages = st->inf_stages; p.row_tiles = row_tiles;
         { TcParams q = p; q.m_tiles = mh; q.row0 = row0; q.Hact = e.Hchunk - row0 * q.ldh; q.Hlo = e.Hchunk_lo - row0 * q.ldh;
           m.A = st->W1_mn; m.Alo = st->W1lo_mn; m.B = Xk; m.Blo = which_x == 2 ? st->Xte_lo_k : st->Xchunk_lo_k; m.C = Xk;
+          const int tiles = e.S * mh * row_tiles;
           KernelTimer t(e, "infer1");
-          tc_lt_kernel<TC_FWD1><<<dim3(1, mh * row_tiles, e.S), LT_THREADS, c.smem, e.stream>>>(m, q);
+          tc_lt_infer_kernel<TC_FWD1><<<dim3(std::min(tiles, 148)), LT_THREADS, st->inf_smem, e.stream>>>(m, q);
           count_launch(e, "infer1"); }
         { TcParams q = p; q.m_tiles = mo; q.row0 = 0;
           if (with_loss) { q.Y = e.Yte + row0 * (int64_t)e.S * e.Op; q.ldy = (int64_t)e.S * e.Op; q.loss = e.d_loss + 1; }
           q.out = out; q.ld_out = ld_out;
           m.A = st->W2_mn; m.Alo = st->W2lo_mn; m.B = st->Hchunk_k; m.Blo = st->Hchunk_lo_k; m.C = st->Hchunk_k;
+          const int tiles = e.S * mo * row_tiles;
           KernelTimer t(e, "infer2");
-          tc_lt_kernel<TC_FWD2><<<dim3(1, mo * row_tiles, e.S), LT_THREADS, c.smem, e.stream>>>(m, q);
+          tc_lt_infer_kernel<TC_FWD2><<<dim3(std::min(tiles, 148)), LT_THREADS, st->inf_smem, e.stream>>>(m, q);
           count_launch(e, "infer2"); }
         return;
     }
