@@ -1682,6 +1682,223 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_big_kernel(const __gr
     DI_TRACE_T0(5);
 }
 
+// ------------------------------------------------------------------------------ ADAM, persistent: tiles overlap
+// tc_adam_big_kernel spends the first 45 % of a tile's life (operand loads over a shared L2, then the MMAs) with the
+// w / m / v stream idle, and the rest with the tensor core idle.  Here one CTA walks several tiles
+// (t = blockIdx.x, + gridDim.x, ...) and overlaps the two halves: tensor memory holds two accumulator stages, so while
+// the sixteen epilogue warps stream tile i's chunks through an 8-stage ring (load by TMA, update in registers, store),
+// the TMA warp already fetches tile i + 1's operand sets into the operand area -- free as soon as tile i's MMAs have
+// been committed -- and the MMA warp fills the other stage.  Same tile, operands, arithmetic and summation order as the
+// resident kernel: results are bit-identical.  Used where throughput counts (many sub-networks per GPU); the resident
+// kernel, one tile per CTA, stays for the latency-bound regime.
+constexpr int ADP_RING = 8;                               // chunk stages
+
+template <bool X3>
+__global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_pers_kernel(const __grid_constant__ AdamMaps maps1,
+                                                                        const __grid_constant__ AdamMaps maps2, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int NSETS = X3 ? 4 : 2;
+    const int nkb = p.nkb_adam;
+    const uint32_t set_bytes = (uint32_t)nkb * A_STAGE_BYTES;
+    uint8_t* set0 = smem;                                           // dout_hi
+    uint8_t* set1 = smem + set_bytes;                               // in_lo   (plain TF32: in)
+    uint8_t* set2 = smem + 2 * (size_t)set_bytes;                   // in_hi
+    uint8_t* set3 = smem + 3 * (size_t)set_bytes;                   // dout_lo
+    uint8_t* ring = smem + (size_t)NSETS * set_bytes;
+    __shared__ uint64_t ops_full[2], ops_empty, tmem_full_bar[2], tmem_empty_bar[2], wfull[ADP_RING], wdone[ADP_RING];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int TMA_WARP = 4 * AD_MAX_GROUPS, MMA_WARP = TMA_WARP + 1;
+    if (threadIdx.x == 0) {
+        mbar_init(&ops_full[0], 1); mbar_init(&ops_full[1], 1); mbar_init(&ops_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4 * AD_MAX_GROUPS); }
+        for (int i = 0; i < ADP_RING; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wdone[i], 4); }
+        fence_barrier_init();
+    }
+    const uint32_t acc_cols = (uint32_t)ADAM_TILE * (p.lo_acc ? 2u : 1u);     // columns of one accumulator stage
+    if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    if (warp != TMA_WARP) pdl_wait();
+    if (p.pdl_early && threadIdx.x == 0) pdl_release();
+    __syncwarp();
+
+    // tile t of this launch -> sub-network, weight matrix, tile origin.  tiles per sub-network: nx1 * mh of W1, then nx2 * mo of W2
+    const int mh = (p.Hp + TILE_M - 1) / TILE_M, mo = (p.Op + TILE_M - 1) / TILE_M, nx2 = (p.Hp + ADAM_TILE - 1) / ADAM_TILE;
+    const int tps = p.nx1 * mh + nx2 * mo;
+    const int n_tiles = p.row_tiles * tps;                // row_tiles: sub-networks of this launch
+    struct Tile { int s, m0, n0, out_dim, a_c0, b_c0, b_c1, nch, wbox; bool second; int64_t row_base; };
+    auto tile_of = [&](int t, Tile& T) {
+        T.s = t / tps + p.s_base;
+        int r = t % tps;
+        T.second = r >= p.nx1 * mh;
+        const SubnetDesc d = p.desc[T.s];
+        int in_dim;
+        if (!T.second) {
+            T.n0 = (r / mh) * ADAM_TILE; T.m0 = (r % mh) * TILE_M; T.out_dim = p.Hp; in_dim = d.Pp;
+            T.a_c0 = T.s * p.Hp + T.m0; T.b_c0 = (int)d.coff + T.n0; T.b_c1 = (int)p.row0; T.row_base = d.coff; T.wbox = p.wbox;
+        } else {
+            r -= p.nx1 * mh;
+            T.n0 = (r / mo) * ADAM_TILE; T.m0 = (r % mo) * TILE_M; T.out_dim = p.Op; in_dim = p.Hp;
+            T.a_c0 = T.s * p.Op + T.m0; T.b_c0 = T.s * p.Hp + T.n0; T.b_c1 = 0; T.row_base = (int64_t)T.s * p.Hp; T.wbox = p.wbox2;
+        }
+        T.nch = (T.m0 < T.out_dim && T.n0 < in_dim) ? min(ADAM_TILE, in_dim - T.n0) / AD_R : 0;    // 0: nothing to do (ragged edge)
+    };
+
+    if (warp == TMA_WARP) {
+        if (elect_one()) {
+            auto load_ops = [&](const Tile& T, bool first_tile) {
+                const AdamMaps* mp = T.second ? &maps2 : &maps1;
+                auto load_a = [&](const CUtensorMap* m, uint8_t* dst, uint64_t* bar) {
+                    for (int kb = 0; kb < nkb; ++kb) load_stage<true>(dst + (size_t)kb * A_STAGE_BYTES, m, bar, T.a_c0, kb * BLOCK_K, TILE_M);
+                };
+                auto load_b = [&](const CUtensorMap* m, uint8_t* dst, uint64_t* bar) {
+                    for (int kb = 0; kb < nkb; ++kb) load_stage<true>(dst + (size_t)kb * A_STAGE_BYTES, m, bar, T.b_c0, T.b_c1 + kb * BLOCK_K, ADAM_TILE);
+                };
+                if constexpr (X3) { mbar_arrive_expect_tx(&ops_full[0], 3u * set_bytes); mbar_arrive_expect_tx(&ops_full[1], set_bytes); }
+                else mbar_arrive_expect_tx(&ops_full[0], 2u * set_bytes);
+                // (the launch's first tile: ADAM follows BWD, which writes dz1 -- the dout of W1 tiles -- and nothing else
+                // read here, so everything but that is requested before waiting for it)
+                if constexpr (X3) { load_b(&mp->Blo, set1, &ops_full[0]); load_b(&mp->B, set2, &ops_full[0]); }
+                else load_b(&mp->B, set1, &ops_full[0]);
+                const bool wait_first = first_tile && !(p.pdl_prefetch && T.second);
+                if (first_tile && !wait_first) { /* dout = dz2: written two grids back */ }
+                if (wait_first) pdl_wait();
+                load_a(&mp->A, set0, &ops_full[0]);
+                if constexpr (X3) load_a(&mp->Alo, set3, &ops_full[1]);
+                if (first_tile && !wait_first) pdl_wait();
+            };
+            int g = 0, i = 0;                             // chunks issued so far (ring position), non-empty tiles so far
+            Tile T, Tn;
+            int t = blockIdx.x;
+            for (; t < n_tiles; t += gridDim.x) { tile_of(t, T); if (T.nch) break; }
+            if (t < n_tiles) load_ops(T, true); else pdl_wait();
+            while (t < n_tiles) {
+                int tn = t + gridDim.x;                   // next non-empty tile of this CTA
+                for (; tn < n_tiles; tn += gridDim.x) { tile_of(tn, Tn); if (Tn.nch) break; }
+                const AdamMaps* mp = T.second ? &maps2 : &maps1;
+                const int tile_floats = AD_R * T.wbox;
+                auto load_chunk = [&](int c) {
+                    const int slot = g % ADP_RING;
+                    if (g >= ADP_RING) mbar_wait(&wdone[slot], ((g / ADP_RING) - 1) & 1, 8);
+                    float* ws = reinterpret_cast<float*>(ring + (size_t)slot * p.ad_stride);
+                    const int32_t r = (int32_t)(T.row_base + T.n0 + c * AD_R);
+                    mbar_arrive_expect_tx(&wfull[slot], 3u * (uint32_t)tile_floats * 4u);
+                    tma_load_2d(ws, &mp->W, &wfull[slot], T.m0, r);
+                    tma_load_2d(ws + tile_floats, &mp->M, &wfull[slot], T.m0, r);
+                    tma_load_2d(ws + 2 * tile_floats, &mp->V, &wfull[slot], T.m0, r);
+                    ++g;
+                };
+                int c = 0;
+                for (; c < min(ADP_RING, T.nch); ++c) load_chunk(c);
+                // this tile's MMAs have read the operand area: the next tile's operands may land
+                mbar_wait(&ops_empty, i & 1, 9);
+                if (tn < n_tiles) load_ops(Tn, false);
+                for (; c < T.nch; ++c) load_chunk(c);
+                t = tn; T = Tn; ++i;
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        if (elect_one()) {
+            const uint32_t idesc = idesc_for(ADAM_TILE, true, true);
+            int i = 0;
+            Tile T;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                tile_of(t, T);
+                if (!T.nch) continue;
+                const int acc = i & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((i >> 1) & 1) ^ 1, 12);
+                tc_fence_after();
+                const uint32_t d_hi = tmem + (uint32_t)acc * acc_cols, d_lo = p.lo_acc ? d_hi + ADAM_TILE : d_hi;
+                auto mma_round = [&](uint32_t dst, const uint8_t* a, const uint8_t* b, bool first) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        const uint32_t sa = smem_u32(a + (size_t)kb * A_STAGE_BYTES);
+                        const uint32_t sb = smem_u32(b + (size_t)kb * A_STAGE_BYTES);
+#pragma unroll
+                        for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
+                            umma_tf32(dst, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (!first || kb || j) ? 1u : 0u);
+                    }
+                };
+                mbar_wait(&ops_full[0], i & 1, 6);
+                tc_fence_after();
+                if constexpr (X3) {
+                    mma_round(d_lo, set0, set1, true);                     // dout_hi in_lo
+                    mma_round(d_hi, set0, set2, p.lo_acc != 0);            // dout_hi in_hi
+                    mbar_wait(&ops_full[1], i & 1, 6);
+                    tc_fence_after();
+                    mma_round(d_lo, set3, set2, false);                    // dout_lo in_hi
+                } else {
+                    mma_round(d_hi, set0, set1, true);
+                }
+                umma_commit(&ops_empty);
+                umma_commit(&tmem_full_bar[acc]);
+                ++i;
+            }
+        }
+    } else {
+        const int quad = warp & 3, grp = warp >> 2;
+        const int fl = quad * 32 + lane;
+        const AdamParams adam = adam_of(p);
+        int g0 = 0, i = 0, n_live = 0;
+        Tile T;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) { tile_of(t, T); n_live += T.nch ? 1 : 0; }
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            tile_of(t, T);
+            if (!T.nch) continue;
+            const int acc = i & 1;
+            const bool f_ok = (T.m0 + fl) < T.out_dim;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_cols;
+            mbar_wait(&tmem_full_bar[acc], (i >> 1) & 1, 4);
+            tc_fence_after();
+            if (i + 1 == n_live && threadIdx.x == 0 && !p.pdl_early) pdl_release();     // the last accumulator of this CTA is complete
+            __syncwarp();
+            float* gw0 = T.second ? p.W2 : p.W1;
+            float* gm0 = T.second ? p.mW2 : p.mW1;
+            float* gv0 = T.second ? p.vW2 : p.vW1;
+            float* gl0 = T.second ? p.W2lo : p.W1lo;
+            for (int c = grp; c < T.nch; c += AD_MAX_GROUPS) {
+                const int g = g0 + c, slot = g % ADP_RING;
+                float gr[AD_R];
+                __syncwarp();
+                tmem_ld8(taddr + c * AD_R, gr);
+                if (X3 && p.lo_acc) {
+                    float gl[AD_R];
+                    tmem_ld8(taddr + ADAM_TILE + c * AD_R, gl);
+#pragma unroll
+                    for (int r = 0; r < AD_R; ++r) gr[r] += gl[r];
+                }
+                mbar_wait(&wfull[slot], (g / ADP_RING) & 1, 7);
+                __syncwarp();
+                if (f_ok) {
+                    const uint32_t base = smem_u32(ring + (size_t)slot * p.ad_stride) + (uint32_t)fl * 4u;
+                    const int64_t off = (T.row_base + T.n0 + (int64_t)c * AD_R) * T.out_dim + T.m0 + fl;
+                    float* gl = gl0 ? gl0 + off : nullptr;
+                    // the loads of adam_chunk are complete before its stores are issued (they feed them), so the stage
+                    // may be handed back right after the call
+                    if (T.wbox == TILE_M && T.out_dim == 256) adam_chunk<TILE_M, 256>(base, gr, adam, gw0 + off, gm0 + off, gv0 + off, gl, 0, 0);
+                    else if (T.wbox == TILE_M && T.out_dim == 512) adam_chunk<TILE_M, 512>(base, gr, adam, gw0 + off, gm0 + off, gv0 + off, gl, 0, 0);
+                    else adam_chunk<0, 0>(base, gr, adam, gw0 + off, gm0 + off, gv0 + off, gl, T.wbox, T.out_dim);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&wdone[slot]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            g0 += T.nch; ++i;
+        }
+        if (n_live == 0 && threadIdx.x == 0 && !p.pdl_early) pdl_release();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct TcState {
     // weights / step buffers (fixed for the life of the engine)
@@ -1736,6 +1953,8 @@ struct TcState {
     int aux_h = 0, aux_y = 0, wbox1 = 0, wbox2 = 0;
     bool adam_direct = true;                               // DEEPIMPUTE_B200_ADAM_STORE=tma selects the in-place ring + TMA stores
     bool adam_big = false;                                 // one-CTA-per-SM ADAM kernel (DEEPIMPUTE_B200_ADAM=ring disables it)
+    bool adam_pers = false;                                // persistent ADAM kernel: several tiles per CTA, overlapped (throughput regime)
+    int adam_tpc = 2, smem_adam_pers = 0;                  // tiles per CTA; shared memory
     bool pdl = true;                                       // programmatic dependent launch along a step's kernel chain (DEEPIMPUTE_B200_PDL=0 disables)
     bool pdl_early = false;                                // DEEPIMPUTE_B200_PDL=2: dependents released before the main loop instead of after it
     bool pdl_early_adam = false;                           // ... the ADAM kernel too (its successor is the next step's FWD1)
@@ -2045,6 +2264,11 @@ bool tc_init(Engine& e) {
         st->adam_big = st->ad_nded >= 1 && (AD_MAX_CHUNKS - st->ad_nded) * st->ad_stride <= ops;
         st->smem_adam_big = ops + st->ad_nded * st->ad_stride + 1024;
         if (const char* v = getenv("DEEPIMPUTE_B200_ADAM")) if (!strcmp(v, "ring")) st->adam_big = false;
+        // persistent form: operand area + 8-stage chunk ring; where throughput counts, i.e. with the converter family
+        st->smem_adam_pers = ops + ADP_RING * st->ad_stride + 1024;
+        st->adam_pers = st->adam_big && st->x3 && !st->lt && st->smem_adam_pers <= 227 * 1024 - 2048;
+        if (const char* v = getenv("DEEPIMPUTE_B200_ADAM")) { if (!strcmp(v, "pers")) st->adam_pers = st->adam_big && st->smem_adam_pers <= 227 * 1024 - 2048; else st->adam_pers = false; }
+        if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_TPC")) st->adam_tpc = std::max(1, std::min(8, atoi(v)));
 
         if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_GROUPS")) st->ad_groups = std::max(1, std::min(AD_MAX_GROUPS, atoi(v)));
     }
@@ -2084,6 +2308,10 @@ bool tc_init(Engine& e) {
     if (st->adam_big) {
         set((const void*)tc_adam_big_kernel<false>, st->smem_adam_big);
         set((const void*)tc_adam_big_kernel<true>, st->smem_adam_big);
+    }
+    if (st->adam_pers) {
+        set((const void*)tc_adam_pers_kernel<false>, st->smem_adam_pers);
+        set((const void*)tc_adam_pers_kernel<true>, st->smem_adam_pers);
     }
 
     if (ce != cudaSuccess) { e.err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return false; }
@@ -2289,7 +2517,16 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam");
     q.ad_nded = st->ad_nded; q.ad_stride = st->ad_stride; q.ad_kg = st->ad_kg;
     { static const bool generic = [] { const char* v = getenv("DEEPIMPUTE_B200_ADAM_GENERIC"); return v && atoi(v) != 0; }(); q.ad_generic = generic ? 1 : 0; }
-    if (st->adam_big) {
+    if (st->adam_pers) {
+        const int nx2 = cdiv(e.Hp, ADAM_TILE);
+        const int tiles = pl.ns * (q.nx1 * mh + nx2 * mo);
+        q.row_tiles = pl.ns;
+        q.tmem_cols = 2 * (q.lo_acc ? 2 * ADAM_TILE : ADAM_TILE);
+        const bool pdl = st->pdl && pl.graph;
+        const dim3 pgrid((unsigned)cdiv(tiles, st->adam_tpc));
+        if (st->x3) launch_k(tc_adam_pers_kernel<true>, pgrid, NTHREADS_BIG, st->smem_adam_pers, pl.main, pdl, m1, m2, q);
+        else launch_k(tc_adam_pers_kernel<false>, pgrid, NTHREADS_BIG, st->smem_adam_pers, pl.main, pdl, m1, m2, q);
+    } else if (st->adam_big) {
         const int nthreads = (4 * st->ad_groups + 2) * 32;
         const bool pdl = st->pdl && pl.graph;
         if (st->x3) launch_k(tc_adam_big_kernel<true>, grid, nthreads, st->smem_adam_big, pl.main, pdl, m1, m2, q);
@@ -2433,7 +2670,7 @@ const char* tc_describe(Engine& e) {
              "fwd/bwd=%s splitk=%d stages=%d/%d adam=%s groups=%d graph=%d pdl=%d%s l2_window=%d (%.1f MB of %.1f MB state, hitRatio %.2f) graph_fallbacks=%lld",
              st->lt ? "lt" : (st->ts ? "ts" : (st->x3 ? "x3-smem" : "tf32")), st->lt ? st->lt_ks : 1,
              st->lt ? st->lt_train.stages : st->fwd1_train[1].stages, st->lt ? st->lt_infer.stages : st->infer.stages,
-             st->adam_big ? "resident" : "ring", st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0,
+             st->adam_pers ? "persistent" : (st->adam_big ? "resident" : "ring"), st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0,
              st->pdl_early_adam ? "(early release, all four kernels)" : (st->pdl_early ? "(early release, fwd/bwd)" : ""), st->l2_window ? 1 : 0,
              st->l2_window ? st->l2_policy.num_bytes * (double)st->l2_policy.hitRatio / 1048576.0 : 0.0,
              e.state_bytes / 1048576.0, st->l2_window ? (double)st->l2_policy.hitRatio : 0.0, (long long)st->graph_fallbacks);
