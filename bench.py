@@ -249,8 +249,15 @@ def load_traffic(workload, kernel, n_pred):
              "fwd1": "tc_kernel<0", "fwd2": "tc_kernel<1", "bwd": "tc_kernel<2"}
     if kernel not in grids:
         return None
+    table = json.load(open(path)).get(workload, {})
+    if kernel == "adam":
+        # the persistent ADAM kernel (the default at many sub-networks per GPU) is launched as a 1-D grid of
+        # ceil(tiles / tiles_per_CTA) CTAs: its capture is keyed by name and sub-network count only
+        for key, val in table.items():
+            if key.startswith("tc_adam_pers_kernel") and key.endswith("S={}".format(S)):
+                return val
     want = "grid ({}, {}, {})".format(*grids[kernel])
-    for key, val in json.load(open(path)).get(workload, {}).items():
+    for key, val in table.items():
         if key.startswith(names[kernel]) and key.endswith(want):
             return val
     return None
