@@ -35,10 +35,13 @@ def test_reference_multinet_test_flow(test_counts):
     np.testing.assert_allclose(out2.values, out.values, rtol=1e-6)
 
 
-def test_fit_predict_matches_oracle_at_fixed_epochs(test_counts):
-    """Config c1 (test.csv, defaults, seed 1234) for 5 epochs: imputed values within 1e-3 relative of the oracle."""
+@pytest.mark.parametrize("math_mode", ["fp32", "tf32x3"])
+def test_fit_predict_matches_oracle_at_fixed_epochs(test_counts, math_mode):
+    """Config c1 (test.csv, defaults, seed 1234) for 5 epochs: imputed values within 1e-3 relative of the oracle --
+    for the strict fp32 kernels and for the default tensor-core mode directly (not via the fp32 path) -- and the
+    held-out metrics of multinet.py:252-262 equal to the oracle's own."""
     raw = test_counts
-    net = MultiNet(seed=1234, ncores=1, max_epochs=5, patience=100, verbose=0, math_mode="fp32")
+    net = MultiNet(seed=1234, ncores=1, max_epochs=5, patience=100, verbose=0, math_mode=math_mode)
     net.fit(raw)
     assert [len(p) for p in net.predictors] == [639, 592, 592, 594, 555, 631]
     got = net.predict(raw, policy="restore")
@@ -70,6 +73,13 @@ def test_fit_predict_matches_oracle_at_fixed_epochs(test_counts):
     imputed_ref = np.expm1(want[:, sel].astype(np.float64))
     rel = np.abs(got.values[:, single] - imputed_ref) / (np.abs(imputed_ref) + 1e-3)
     assert rel[zero].max() < 1e-3
+    # held-out metrics (multinet.py:252-262): Pearson r and MSE over the originally non-zero entries of the test cells
+    from scipy.stats import pearsonr
+    y_true = np.hstack(Yte).reshape(-1)
+    y_hat = np.hstack(ref.forward(Xte)).reshape(-1)
+    seen = y_true > 0
+    assert net.test_metrics["correlation"] == pytest.approx(pearsonr(y_true[seen], y_hat[seen])[0], rel=1e-5)
+    assert net.test_metrics["MSE"] == pytest.approx(np.sum((y_true[seen] - y_hat[seen]) ** 2) / seen.sum(), rel=1e-4)
 
 
 def test_tensor_core_modes_track_the_fp32_path(test_counts):
