@@ -254,7 +254,7 @@ def load_traffic(workload, kernel, n_pred):
         # the persistent ADAM kernel (the default at many sub-networks per GPU) is launched as a 1-D grid of
         # ceil(tiles / tiles_per_CTA) CTAs
         tiles = S * (cd(max_pp, 128) * cd(HIDDEN, 128) + cd(HIDDEN, 128) * cd(OUT, 128))
-        want = "grid ({}, 1, 1)".format(cd(tiles, int(os.environ.get("DEEPIMPUTE_B200_ADAM_TPC", "2"))))
+        want = "grid ({}, 1, 1)".format(min(148, cd(tiles, int(os.environ.get("DEEPIMPUTE_B200_ADAM_TPC", "2")))))
         for key, val in table.items():
             if key.startswith("tc_adam_pers_kernel") and key.endswith(want):
                 return val

@@ -2523,7 +2523,9 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
         q.row_tiles = pl.ns;
         q.tmem_cols = 2 * (q.lo_acc ? 2 * ADAM_TILE : ADAM_TILE);
         const bool pdl = st->pdl && pl.graph;
-        const dim3 pgrid((unsigned)cdiv(tiles, st->adam_tpc));
+        // adam_tpc tiles per CTA for the small group launches of the epoch graph; never more CTAs than SMs (a full-width
+        // launch is then one persistent CTA per SM walking ~5 tiles)
+        const dim3 pgrid((unsigned)std::min(cdiv(tiles, st->adam_tpc), 148));
         if (st->x3) launch_k(tc_adam_pers_kernel<true>, pgrid, NTHREADS_BIG, st->smem_adam_pers, pl.main, pdl, m1, m2, q);
         else launch_k(tc_adam_pers_kernel<false>, pgrid, NTHREADS_BIG, st->smem_adam_pers, pl.main, pdl, m1, m2, q);
     } else if (st->adam_big) {
