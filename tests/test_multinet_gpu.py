@@ -133,3 +133,36 @@ def test_small_inputs_and_user_gene_list():
     assert net.targets.shape == (1, 16)
     out = net.predict(raw, imputed_only=True)
     assert out.shape[0] == 90 and set(raw.columns[:10]) <= set(out.columns)
+
+
+def test_n_pred_route_on_the_gpu_matches_the_host_route(test_counts):
+    """``fit(n_pred=...)`` caps the predictor candidates at the n_pred genes with the largest std/mean (multinet.py:25-29).
+    The device route (di_corr_topk with that candidate list; rows = all targets) must choose the predictors the host
+    route chooses, and the model must train and predict with them."""
+    raw = test_counts.iloc[:, :1500]
+    kw = dict(seed=7, ncores=1, max_epochs=2, patience=100, verbose=0, sub_outputdim=256)
+    host = MultiNet(predictor_engine="host", **kw).fit(raw, n_pred=300, NN_lim=512)
+    dev = MultiNet(predictor_engine="gpu", **kw).fit(raw, n_pred=300, NN_lim=512)
+    assert dev.timings["predictor_engine"] == "gpu" and host.timings["predictor_engine"] == "host"
+    np.testing.assert_array_equal(host.targets, dev.targets)
+    same = sum(len(np.intersect1d(a, b)) for a, b in zip(host.predictors, dev.predictors))
+    total = sum(len(p) for p in host.predictors)
+    assert same >= 0.995 * total                                     # fp32 vs float64 correlations: ties only
+    assert max(len(p) for p in dev.predictors) <= 300
+    out = dev.predict(raw)
+    assert out.shape == raw.shape and np.isfinite(out.values).all()
+
+
+def test_integer_gene_labels_survive_save_and_load(tmp_path):
+    """A frame whose gene labels are integers: a fresh object pointed at the saved model must find its genes again
+    (the labels are stored with their dtype, not as strings)."""
+    raw = synthetic_counts(120, 90, seed=6)
+    raw.columns = np.arange(1000, 1000 + raw.shape[1])
+    kw = dict(ncores=1, sub_outputdim=16, max_epochs=2, verbose=0, output_prefix=str(tmp_path),
+              architecture=[{"type": "dense", "neurons": 12, "activation": "relu"}, {"type": "dropout", "rate": 0.2}])
+    net = MultiNet(**kw)
+    net.fit(raw, NN_lim=30, minVMR=0.0)
+    out = net.predict(raw)
+    again = MultiNet(**kw)
+    out2 = again.predict(raw)
+    np.testing.assert_allclose(out2.values, out.values, rtol=1e-6)
