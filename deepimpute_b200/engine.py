@@ -353,15 +353,21 @@ class Engine:
         meta = dict(n_pred=np.asarray(self.n_pred), hidden=self.H, sub_outputdim=self.O, batch_size=self.B,
                     learning_rate=self.learning_rate, dropout_rate=self.dropout_rate, seed=self.seed,
                     subnet_ids=np.asarray(self.subnet_ids))
+        def portable(a):
+            """Labels as an array np.savez can store without pickling, keeping their type: integer gene names stay
+            integers (also when they arrive in an object array), everything else becomes text."""
+            a = np.asarray(a)
+            if a.dtype == object and a.size and all(isinstance(x, (int, np.integer)) and not isinstance(x, bool) for x in a.ravel()):
+                return a.astype(np.int64)
+            return a.astype(str) if a.dtype.kind in "OUS" else a
+
         for k, v in extra.items():
             if isinstance(v, (list, tuple)):
                 arrays["extra_{}_n".format(k)] = np.asarray(len(v))
                 for i, a in enumerate(v):
-                    a = np.asarray(a)       # gene labels keep their type (integer column names stay integers)
-                    arrays["extra_{}_{}".format(k, i)] = a.astype(str) if a.dtype.kind in "OUS" else a
+                    arrays["extra_{}_{}".format(k, i)] = portable(a)
             else:
-                a = np.asarray(v)
-                arrays["extra_" + k] = a.astype(str) if a.dtype.kind in "OUS" else a
+                arrays["extra_" + k] = portable(v)
         np.savez(path, **arrays, **{"meta_" + k: np.asarray(v) for k, v in meta.items()})
 
     @staticmethod
