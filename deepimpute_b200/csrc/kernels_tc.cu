@@ -1899,6 +1899,207 @@ __global__ void __launch_bounds__(NTHREADS_BIG, 1) tc_adam_pers_kernel(const __g
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
+// --------------------------------------------------------------- ADAM, persistent, any batch: operands in passes
+// The persistent kernel above needs all four operand sets of a tile resident at once (batch <= 64).  For larger batches
+// (BASELINE.json configs[4]: 256) the K loop of the weight-gradient GEMM runs in passes of ADQ_KG K blocks through the
+// same 128 KB operand area: the operand producer refills it as soon as the MMAs of the previous pass are committed and
+// the accumulators (a b / small products, see acc_sum16) carry across passes.  A SECOND producer warp owns the w / m / v
+// chunk ring, so that a full ring never delays the operands of the next pass.  Everything else -- two accumulator stages
+// in tensor memory, the epilogue of tile i under the passes of tile i + 1 -- is tc_adam_pers_kernel.
+// Replaces the ring kernel (tc_adam_kernel), which reloads its operand buffers twelve times per tile with the
+// w / m / v stream idle: 191 us per full-width launch at configs[4].
+constexpr int ADQ_KG = 2;
+constexpr int NTHREADS_PERS2 = (4 * AD_MAX_GROUPS + 3) * 32;
+
+__global__ void __launch_bounds__(NTHREADS_PERS2, 1) tc_adam_pers2_kernel(const __grid_constant__ AdamMaps maps1,
+                                                                          const __grid_constant__ AdamMaps maps2, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int nkb = p.nkb_adam;
+    const int npass = (nkb + ADQ_KG - 1) / ADQ_KG;
+    constexpr uint32_t set_bytes = ADQ_KG * A_STAGE_BYTES;
+    uint8_t* set0 = smem;                                           // dout_hi
+    uint8_t* set1 = smem + set_bytes;                               // in_lo
+    uint8_t* set2 = smem + 2 * (size_t)set_bytes;                   // in_hi
+    uint8_t* set3 = smem + 3 * (size_t)set_bytes;                   // dout_lo
+    uint8_t* ring = smem + 4 * (size_t)set_bytes;
+    __shared__ uint64_t ops_full, ops_empty, tmem_full_bar[2], tmem_empty_bar[2], wfull[ADP_RING], wdone[ADP_RING];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int OPS_WARP = 4 * AD_MAX_GROUPS, MMA_WARP = OPS_WARP + 1, CHUNK_WARP = OPS_WARP + 2;
+    if (threadIdx.x == 0) {
+        mbar_init(&ops_full, 1); mbar_init(&ops_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4 * AD_MAX_GROUPS); }
+        for (int i = 0; i < ADP_RING; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wdone[i], 4); }
+        fence_barrier_init();
+    }
+    constexpr uint32_t acc_cols = 2 * ADAM_TILE;          // a b tile + small-product tile
+    if (warp == 0) tmem_alloc(&tmem_base_slot, 512u);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    // the chunk producer reads only what the previous optimiser step wrote: it does not wait for the grid ahead
+    if (warp != CHUNK_WARP) pdl_wait();
+    if (p.pdl_early && threadIdx.x == 0) pdl_release();
+    __syncwarp();
+
+    const int mh = (p.Hp + TILE_M - 1) / TILE_M, mo = (p.Op + TILE_M - 1) / TILE_M, nx2 = (p.Hp + ADAM_TILE - 1) / ADAM_TILE;
+    const int tps = p.nx1 * mh + nx2 * mo;
+    const int n_tiles = p.row_tiles * tps;
+    struct Tile { int s, m0, n0, out_dim, a_c0, b_c0, b_c1, nch, wbox; bool second; int64_t row_base; };
+    auto tile_of = [&](int t, Tile& T) {
+        T.s = t / tps + p.s_base;
+        int r = t % tps;
+        T.second = r >= p.nx1 * mh;
+        const SubnetDesc d = p.desc[T.s];
+        int in_dim;
+        if (!T.second) {
+            T.n0 = (r / mh) * ADAM_TILE; T.m0 = (r % mh) * TILE_M; T.out_dim = p.Hp; in_dim = d.Pp;
+            T.a_c0 = T.s * p.Hp + T.m0; T.b_c0 = (int)d.coff + T.n0; T.b_c1 = (int)p.row0; T.row_base = d.coff; T.wbox = p.wbox;
+        } else {
+            r -= p.nx1 * mh;
+            T.n0 = (r / mo) * ADAM_TILE; T.m0 = (r % mo) * TILE_M; T.out_dim = p.Op; in_dim = p.Hp;
+            T.a_c0 = T.s * p.Op + T.m0; T.b_c0 = T.s * p.Hp + T.n0; T.b_c1 = 0; T.row_base = (int64_t)T.s * p.Hp; T.wbox = p.wbox2;
+        }
+        T.nch = (T.m0 < T.out_dim && T.n0 < in_dim) ? min(ADAM_TILE, in_dim - T.n0) / AD_R : 0;
+    };
+
+    if (warp == OPS_WARP) {
+        // ===== operand producer: (tile, pass) after (tile, pass), one refill of the operand area each =====
+        if (elect_one()) {
+            int q = 0;                                    // passes issued so far
+            Tile T;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                tile_of(t, T);
+                if (!T.nch) continue;
+                const AdamMaps* mp = T.second ? &maps2 : &maps1;
+                for (int pass = 0; pass < npass; ++pass, ++q) {
+                    const int kb0 = pass * ADQ_KG, cnt = min(ADQ_KG, nkb - kb0);
+                    if (q > 0) mbar_wait(&ops_empty, (q - 1) & 1, 9);          // the MMAs of the previous pass have read the area
+                    mbar_arrive_expect_tx(&ops_full, 4u * (uint32_t)cnt * A_STAGE_BYTES);
+                    for (int k = 0; k < cnt; ++k) {
+                        const int row = (kb0 + k) * BLOCK_K;
+                        load_stage<true>(set0 + (size_t)k * A_STAGE_BYTES, &mp->A, &ops_full, T.a_c0, row, TILE_M);
+                        load_stage<true>(set3 + (size_t)k * A_STAGE_BYTES, &mp->Alo, &ops_full, T.a_c0, row, TILE_M);
+                        load_stage<true>(set1 + (size_t)k * A_STAGE_BYTES, &mp->Blo, &ops_full, T.b_c0, T.b_c1 + row, ADAM_TILE);
+                        load_stage<true>(set2 + (size_t)k * A_STAGE_BYTES, &mp->B, &ops_full, T.b_c0, T.b_c1 + row, ADAM_TILE);
+                    }
+                }
+            }
+        }
+    } else if (warp == CHUNK_WARP) {
+        // ===== chunk producer: the w / m / v ring, tile after tile =====
+        if (elect_one()) {
+            int g = 0;
+            Tile T;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                tile_of(t, T);
+                if (!T.nch) continue;
+                const AdamMaps* mp = T.second ? &maps2 : &maps1;
+                const int tile_floats = AD_R * T.wbox;
+                for (int c = 0; c < T.nch; ++c, ++g) {
+                    const int slot = g % ADP_RING;
+                    if (g >= ADP_RING) mbar_wait(&wdone[slot], ((g / ADP_RING) - 1) & 1, 8);
+                    float* ws = reinterpret_cast<float*>(ring + (size_t)slot * p.ad_stride);
+                    const int32_t r = (int32_t)(T.row_base + T.n0 + c * AD_R);
+                    mbar_arrive_expect_tx(&wfull[slot], 3u * (uint32_t)tile_floats * 4u);
+                    tma_load_2d(ws, &mp->W, &wfull[slot], T.m0, r);
+                    tma_load_2d(ws + tile_floats, &mp->M, &wfull[slot], T.m0, r);
+                    tma_load_2d(ws + 2 * tile_floats, &mp->V, &wfull[slot], T.m0, r);
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        if (elect_one()) {
+            const uint32_t idesc = idesc_for(ADAM_TILE, true, true);
+            int i = 0, q = 0;
+            Tile T;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                tile_of(t, T);
+                if (!T.nch) continue;
+                const int acc = i & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((i >> 1) & 1) ^ 1, 12);
+                tc_fence_after();
+                const uint32_t d_hi = tmem + (uint32_t)acc * acc_cols, d_lo = d_hi + ADAM_TILE;
+                for (int pass = 0; pass < npass; ++pass, ++q) {
+                    const int cnt = min(ADQ_KG, nkb - pass * ADQ_KG);
+                    mbar_wait(&ops_full, q & 1, 6);
+                    tc_fence_after();
+                    auto mma_round = [&](uint32_t dst, const uint8_t* a, const uint8_t* b, bool fresh) {
+                        for (int k = 0; k < cnt; ++k) {
+                            const uint32_t sa = smem_u32(a + (size_t)k * A_STAGE_BYTES);
+                            const uint32_t sb = smem_u32(b + (size_t)k * A_STAGE_BYTES);
+#pragma unroll
+                            for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
+                                umma_tf32(dst, stage_desc<true>(sa, j), stage_desc<true>(sb, j), idesc, (!fresh || k || j) ? 1u : 0u);
+                        }
+                    };
+                    mma_round(d_lo, set0, set1, pass == 0);                // dout_hi in_lo
+                    mma_round(d_hi, set0, set2, pass == 0);                // dout_hi in_hi
+                    mma_round(d_lo, set3, set2, false);                    // dout_lo in_hi
+                    umma_commit(&ops_empty);
+                }
+                umma_commit(&tmem_full_bar[acc]);
+                ++i;
+            }
+        }
+    } else {
+        const int quad = warp & 3, grp = warp >> 2;
+        const int fl = quad * 32 + lane;
+        const AdamParams adam = adam_of(p);
+        int g0 = 0, i = 0, n_live = 0;
+        Tile T;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) { tile_of(t, T); n_live += T.nch ? 1 : 0; }
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            tile_of(t, T);
+            if (!T.nch) continue;
+            const int acc = i & 1;
+            const bool f_ok = (T.m0 + fl) < T.out_dim;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_cols;
+            mbar_wait(&tmem_full_bar[acc], (i >> 1) & 1, 4);
+            tc_fence_after();
+            if (i + 1 == n_live && threadIdx.x == 0 && !p.pdl_early) pdl_release();
+            __syncwarp();
+            float* gw0 = T.second ? p.W2 : p.W1;
+            float* gm0 = T.second ? p.mW2 : p.mW1;
+            float* gv0 = T.second ? p.vW2 : p.vW1;
+            float* gl0 = T.second ? p.W2lo : p.W1lo;
+            for (int c = grp; c < T.nch; c += AD_MAX_GROUPS) {
+                const int g = g0 + c, slot = g % ADP_RING;
+                float gr[AD_R], gl_[AD_R];
+                __syncwarp();
+                tmem_ld8(taddr + c * AD_R, gr);
+                tmem_ld8(taddr + ADAM_TILE + c * AD_R, gl_);
+#pragma unroll
+                for (int r = 0; r < AD_R; ++r) gr[r] += gl_[r];
+                mbar_wait(&wfull[slot], (g / ADP_RING) & 1, 7);
+                __syncwarp();
+                if (f_ok) {
+                    const uint32_t base = smem_u32(ring + (size_t)slot * p.ad_stride) + (uint32_t)fl * 4u;
+                    const int64_t off = (T.row_base + T.n0 + (int64_t)c * AD_R) * T.out_dim + T.m0 + fl;
+                    float* gl = gl0 ? gl0 + off : nullptr;
+                    if (T.wbox == TILE_M && T.out_dim == 256) adam_chunk<TILE_M, 256>(base, gr, adam, gw0 + off, gm0 + off, gv0 + off, gl, 0, 0);
+                    else if (T.wbox == TILE_M && T.out_dim == 512) adam_chunk<TILE_M, 512>(base, gr, adam, gw0 + off, gm0 + off, gv0 + off, gl, 0, 0);
+                    else adam_chunk<0, 0>(base, gr, adam, gw0 + off, gm0 + off, gv0 + off, gl, T.wbox, T.out_dim);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&wdone[slot]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            g0 += T.nch; ++i;
+        }
+        if (n_live == 0 && threadIdx.x == 0 && !p.pdl_early) pdl_release();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct TcState {
     // weights / step buffers (fixed for the life of the engine)
@@ -1955,6 +2156,8 @@ struct TcState {
     bool adam_big = false;                                 // one-CTA-per-SM ADAM kernel (DEEPIMPUTE_B200_ADAM=ring disables it)
     bool adam_pers = false;                                // persistent ADAM kernel: several tiles per CTA, overlapped (throughput regime)
     int adam_tpc = 2, smem_adam_pers = 0;                  // tiles per CTA; shared memory
+    bool adam_pers2 = false;                               // ... its any-batch form (operands in passes): batches above 64, tf32x3
+    int smem_adam_pers2 = 0;
     bool pdl = true;                                       // programmatic dependent launch along a step's kernel chain (DEEPIMPUTE_B200_PDL=0 disables)
     bool pdl_early = false;                                // DEEPIMPUTE_B200_PDL=2: dependents released before the main loop instead of after it
     bool pdl_early_adam = false;                           // ... the ADAM kernel too (its successor is the next step's FWD1)
@@ -2269,6 +2472,10 @@ bool tc_init(Engine& e) {
         st->adam_pers = st->adam_big && st->x3 && !st->lt && st->smem_adam_pers <= 227 * 1024 - 2048;
         if (const char* v = getenv("DEEPIMPUTE_B200_ADAM")) { if (!strcmp(v, "pers")) st->adam_pers = st->adam_big && st->smem_adam_pers <= 227 * 1024 - 2048; else st->adam_pers = false; }
         if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_TPC")) st->adam_tpc = std::max(1, std::min(8, atoi(v)));
+        // batches above 64 (the four operand sets no longer fit): the pass-wise persistent kernel instead of the ring kernel
+        st->smem_adam_pers2 = 4 * ADQ_KG * (int)A_STAGE_BYTES + ADP_RING * st->ad_stride + 1024;
+        st->adam_pers2 = st->x3 && !st->adam_big && nkb > ADQ_KG && st->smem_adam_pers2 <= 227 * 1024 - 2048;
+        if (const char* v = getenv("DEEPIMPUTE_B200_ADAM")) if (!strcmp(v, "ring")) st->adam_pers2 = false;
 
         if (const char* v = getenv("DEEPIMPUTE_B200_ADAM_GROUPS")) st->ad_groups = std::max(1, std::min(AD_MAX_GROUPS, atoi(v)));
     }
@@ -2313,6 +2520,7 @@ bool tc_init(Engine& e) {
         set((const void*)tc_adam_pers_kernel<false>, st->smem_adam_pers);
         set((const void*)tc_adam_pers_kernel<true>, st->smem_adam_pers);
     }
+    if (st->adam_pers2) set((const void*)tc_adam_pers2_kernel, st->smem_adam_pers2);
 
     if (ce != cudaSuccess) { e.err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return false; }
     return true;
@@ -2517,7 +2725,15 @@ void launch_step(Engine& e, TcState* st, const StepArgs& a, int which_x, const S
     KernelTimer* t = pl.graph ? nullptr : new KernelTimer(e, "adam");
     q.ad_nded = st->ad_nded; q.ad_stride = st->ad_stride; q.ad_kg = st->ad_kg;
     { static const bool generic = [] { const char* v = getenv("DEEPIMPUTE_B200_ADAM_GENERIC"); return v && atoi(v) != 0; }(); q.ad_generic = generic ? 1 : 0; }
-    if (st->adam_pers) {
+    if (st->adam_pers2) {
+        const int nx2 = cdiv(e.Hp, ADAM_TILE);
+        const int tiles = pl.ns * (q.nx1 * mh + nx2 * mo);
+        q.row_tiles = pl.ns; q.lo_acc = 1; q.tmem_cols = 512;
+        // throughput regime: adam_tpc tiles per CTA; latency-bound regime (LT family): one
+        const int tpc = st->lt ? 1 : st->adam_tpc;
+        launch_k(tc_adam_pers2_kernel, dim3((unsigned)std::min(cdiv(tiles, tpc), 148)), NTHREADS_PERS2, st->smem_adam_pers2, pl.main,
+                 st->pdl && pl.graph, m1, m2, q);
+    } else if (st->adam_pers) {
         const int nx2 = cdiv(e.Hp, ADAM_TILE);
         const int tiles = pl.ns * (q.nx1 * mh + nx2 * mo);
         q.row_tiles = pl.ns;
@@ -2672,7 +2888,7 @@ const char* tc_describe(Engine& e) {
              "fwd/bwd=%s splitk=%d stages=%d/%d adam=%s groups=%d graph=%d pdl=%d%s l2_window=%d (%.1f MB of %.1f MB state, hitRatio %.2f) graph_fallbacks=%lld",
              st->lt ? "lt" : (st->ts ? "ts" : (st->x3 ? "x3-smem" : "tf32")), st->lt ? st->lt_ks : 1,
              st->lt ? st->lt_train.stages : st->fwd1_train[1].stages, st->lt ? st->lt_infer.stages : st->infer.stages,
-             st->adam_pers ? "persistent" : (st->adam_big ? "resident" : "ring"), st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0,
+             st->adam_pers2 ? "persistent-passes" : (st->adam_pers ? "persistent" : (st->adam_big ? "resident" : "ring")), st->n_groups, st->use_graph ? 1 : 0, st->pdl ? 1 : 0,
              st->pdl_early_adam ? "(early release, all four kernels)" : (st->pdl_early ? "(early release, fwd/bwd)" : ""), st->l2_window ? 1 : 0,
              st->l2_window ? st->l2_policy.num_bytes * (double)st->l2_policy.hitRatio / 1048576.0 : 0.0,
              e.state_bytes / 1048576.0, st->l2_window ? (double)st->l2_policy.hitRatio : 0.0, (long long)st->graph_fallbacks);

@@ -13,7 +13,8 @@ from oracle.multinet_oracle import OracleNet, stage
 H, O, RATE, SEED = 256, 512, 0.2, 1234
 rng = np.random.default_rng(11)
 n_pred = [540, 513, 600]
-N, G = 40 * 64 - 17 + 128, 2400
+BATCH = int(os.environ.get("FA_BATCH", "64"))
+N, G = 40 * BATCH - 17 + 128, 2400
 lam = rng.gamma(0.6, 3.0, size=(1, G)) * rng.gamma(2.0, 0.5, size=(N, 1))
 norm = np.log1p(rng.poisson(lam)).astype(np.float32)
 perm = rng.permutation(G)
@@ -21,8 +22,9 @@ targ = perm[:3 * O].reshape(3, O).astype(np.int32)
 pred_idx = [rng.choice(perm[3 * O:], p, replace=False).astype(np.int32) for p in n_pred]
 tr, te = np.arange(N - 128, dtype=np.int32), np.arange(N - 128, N, dtype=np.int32)
 EPOCHS = int(os.environ.get("FA_EPOCHS", "2"))
+LR = float(os.environ.get("FA_LR", "1e-3"))
 
-ref = OracleNet(n_pred, H, O, learning_rate=1e-3, batch_size=64, dropout_rate=RATE, seed=SEED)
+ref = OracleNet(n_pred, H, O, learning_rate=LR, batch_size=BATCH, dropout_rate=RATE, seed=SEED)
 Xtr, Ytr = stage(norm, pred_idx, targ, tr)
 step = 0
 for epoch in range(EPOCHS):
@@ -49,7 +51,7 @@ for name, env in CASES:
     for k in KNOBS:
         os.environ.pop(k, None)
     os.environ.update(env)
-    eng = Engine(n_pred, hidden=H, sub_outputdim=O, learning_rate=1e-3, batch_size=64, dropout_rate=RATE, seed=SEED)
+    eng = Engine(n_pred, hidden=H, sub_outputdim=O, learning_rate=LR, batch_size=BATCH, dropout_rate=RATE, seed=SEED)
     eng.set_data(norm, pred_idx, targ)
     eng.set_split(tr, te)
     t0 = time.perf_counter()
