@@ -33,12 +33,12 @@ want = np.hstack(ref.forward(stage(norm, pred_idx, targ, np.arange(N))[0]))
 want_w = ref.get_weights()
 
 KNOBS = ["DEEPIMPUTE_B200_LT", "DEEPIMPUTE_B200_SPLITK", "DEEPIMPUTE_B200_TS", "DEEPIMPUTE_B200_PDL", "DEEPIMPUTE_B200_GRAPH",
-         "DEEPIMPUTE_B200_PDL_PREFETCH", "DEEPIMPUTE_B200_ADAM", "DEEPIMPUTE_B200_ADAM_VEC", "DEEPIMPUTE_B200_GROUPS", "DEEPIMPUTE_B200_MATH"]
+         "DEEPIMPUTE_B200_PDL_PREFETCH", "DEEPIMPUTE_B200_ADAM", "DEEPIMPUTE_B200_EXPERIMENT", "DEEPIMPUTE_B200_ADAM_VEC", "DEEPIMPUTE_B200_GROUPS", "DEEPIMPUTE_B200_MATH"]
 CASES = [
     ("lt", dict(DEEPIMPUTE_B200_LT="1", DEEPIMPUTE_B200_SPLITK="1")),
-    ("lt adam32", dict(DEEPIMPUTE_B200_LT="1", DEEPIMPUTE_B200_SPLITK="1", DEEPIMPUTE_B200_ADAM_VEC="0")),
+    ("lt split4", dict(DEEPIMPUTE_B200_LT="1", DEEPIMPUTE_B200_SPLITK="4")),
     ("conv ts", dict(DEEPIMPUTE_B200_LT="0")),
-    ("conv ts adam32", dict(DEEPIMPUTE_B200_LT="0", DEEPIMPUTE_B200_ADAM_VEC="0")),
+    ("conv + exact fp32 dW", dict(DEEPIMPUTE_B200_LT="0", DEEPIMPUTE_B200_EXPERIMENT="2")),
     ("conv smem", dict(DEEPIMPUTE_B200_LT="0", DEEPIMPUTE_B200_TS="0")),
     ("conv ts nopdl", dict(DEEPIMPUTE_B200_LT="0", DEEPIMPUTE_B200_PDL="0")),
     ("conv ts noprefetch", dict(DEEPIMPUTE_B200_LT="0", DEEPIMPUTE_B200_PDL_PREFETCH="0")),
