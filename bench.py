@@ -226,6 +226,20 @@ def step_work(n_pred, B):
             sum(B * (4 * p * H + 6 * H * O) for p in n_pred))
 
 
+def workload_config(wl, epochs):
+    """The ``config`` object of the JSON line: what is computed, not how -- both arms print exactly this."""
+    n_pred_all = wl.get("n_pred_all") or [len(p) for p in wl["pred_idx"]]
+    n_train = len(wl["train_rows"])
+    steps_per_epoch = -(-n_train // wl["B"])
+    epoch_bytes = step_work(n_pred_all, wl["B"])[0] * steps_per_epoch
+    return {"workload": wl["desc"], "epochs_per_step": epochs, "batch_size": wl["B"],
+            "sub_networks": len(n_pred_all), "hidden": HIDDEN, "sub_outputdim": OUT,
+            "predictors_per_subnet": [int(min(n_pred_all)), int(max(n_pred_all))],
+            "adam_steps_per_epoch": steps_per_epoch,
+            "l2": "no flush between steps: inputs larger than L2 ({:.1f} GB of weights + Adam state + staged batches "
+                  "stream per epoch)".format(epoch_bytes / 1e9)}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -547,14 +561,13 @@ def main():
             "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "epochs_per_step": args.epochs, "batch_size": wl["B"],
-                       "sub_networks": len(wl["pred_idx"]), "hidden": HIDDEN, "sub_outputdim": OUT,
-                       "note": "restated reference (TensorFlow/Keras unavailable offline): torch-CPU fp32, one "
-                               "matmul per layer per branch.  Each step MEASURES the staging gathers, one full epoch, the "
-                               "validation forward and the predict pass of cpu_baseline.sample's sub-networks and scales "
-                               "by the stated factor; ms_per_step is that extrapolated fit+predict time",
-                       "sampled_seconds_per_step": base.get("sampled_seconds"),
-                       "extrapolation_factor": base.get("extrapolation_factor")},
+            "config": workload_config(wl, args.epochs),
+            "arm": {"note": "restated reference (TensorFlow/Keras unavailable offline): torch-CPU fp32, one "
+                            "matmul per layer per branch.  Each step MEASURES the staging gathers, one full epoch, the "
+                            "validation forward and the predict pass of cpu_baseline.sample's sub-networks and scales "
+                            "by the stated factor; ms_per_step is that extrapolated fit+predict time",
+                    "sampled_seconds_per_step": base.get("sampled_seconds"),
+                    "extrapolation_factor": base.get("extrapolation_factor")},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -738,17 +751,13 @@ def main():
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3 (error-compensated TF32, fp32 accumulate)"}[math_mode], "data": "synthetic",
-            "config": {"workload": wl["desc"], "epochs_per_step": args.epochs, "batch_size": B,
-                       "sub_networks": S_all, "hidden": HIDDEN, "sub_outputdim": OUT,
-                       "predictors_per_subnet": [int(min(n_pred_all)), int(max(n_pred_all))],
-                       "adam_steps_per_epoch": steps_per_epoch, "math_mode": math_mode,
-                       "parallelism": "sub-networks sharded over {} GPU(s)".format(world) if not args.emulate_shard else
-                                      "EMULATION of rank {} of a sharded run on one GPU: {} of {} sub-networks, no collectives"
-                                      .format(args.emulate_shard, len(mine), S_all),
-                       "epoch_driver": "one CUDA-graph launch per epoch over sub-network groups on concurrent streams; "
-                                       "roofline.kernels are timed in a separate launch-by-launch epoch",
-                       "l2": "inputs larger than L2: {:.1f} GB of weights+Adam state+staged batches stream per epoch"
-                             .format((step_bytes * steps_per_epoch) / 1e9)},
+            "config": workload_config(wl, args.epochs),
+            "arm": {"math_mode": math_mode,
+                    "parallelism": "sub-networks sharded over {} GPU(s)".format(world) if not args.emulate_shard else
+                                   "EMULATION of rank {} of a sharded run on one GPU: {} of {} sub-networks, no collectives"
+                                   .format(args.emulate_shard, len(mine), S_all),
+                    "epoch_driver": "one CUDA-graph launch per epoch over sub-network groups on concurrent streams; "
+                                    "roofline.kernels are timed in a separate launch-by-launch epoch"},
             "clocks": clocks.summary(),
             "e2e": {"value": N * G / e2e_s, "unit": unit, "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -45,3 +45,15 @@ def test_reference_arm_line_is_complete():
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     # the value is N * G / (extrapolated fit + predict seconds)
     assert abs(line["value"] * line["ms_per_step"] * 1e-3 - 2000 * 1500) < 1.0
+    # both arms print the same ``config`` object (what is computed); how an arm computes it goes under "arm"
+    assert line["config"] == bench.workload_config(bench.build_workload("tiny", "cpu"), 2)
+    assert set(line["config"]) == {"workload", "epochs_per_step", "batch_size", "sub_networks", "hidden", "sub_outputdim",
+                                   "predictors_per_subnet", "adam_steps_per_epoch", "l2"}
+    assert line["arm"]["extrapolation_factor"] == base["extrapolation_factor"]
+
+
+def test_config_of_a_rank_is_the_config_of_the_job():
+    """Sharded runs: the per-rank workload describes the whole job in ``config`` (rank 0 prints it)."""
+    full = bench.workload_config(bench.build_workload("tiny", "cpu"), 20)
+    part = bench.workload_config(bench.build_workload("tiny", "cpu", 3, 0), 20)
+    assert full == part
