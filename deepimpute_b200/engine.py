@@ -49,6 +49,35 @@ def epoch_permutation(seed, epoch, n):
     return np.random.default_rng([int(seed), 0x5EED, int(epoch)]).permutation(n).astype(np.int32)
 
 
+class PermutationPrefetcher:
+    """Visiting orders one epoch ahead of the GPU.
+
+    Drawing the permutation of ~50k training rows costs about a millisecond of host time; ``di_train_epoch`` blocks
+    until the epoch is done and ctypes releases the GIL meanwhile, so a helper thread draws the order of epoch e + 1
+    while the device runs epoch e.  ``perm_fn(epoch)`` must be a pure function of the epoch number (it is:
+    ``epoch_permutation``), so which thread evaluates it -- and an order drawn for an epoch that early stopping never
+    runs -- changes nothing.
+    """
+
+    def __init__(self, perm_fn, n_epochs=None):
+        from concurrent.futures import ThreadPoolExecutor
+        self._fn = perm_fn
+        self._end = n_epochs                    # never ask perm_fn for an epoch at or beyond this one
+        self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="di-perm")
+        self._next = None                       # (epoch, future)
+
+    def get(self, epoch):
+        nxt, self._next = self._next, None
+        perm = nxt[1].result() if (nxt is not None and nxt[0] == epoch) else self._fn(epoch)
+        if self._end is None or epoch + 1 < self._end:
+            self._next = (epoch + 1, self._pool.submit(self._fn, epoch + 1))
+        return perm
+
+    def close(self):
+        self._next = None
+        self._pool.shutdown(wait=False, cancel_futures=True)
+
+
 class Engine:
     def __init__(self, inputdims, hidden=256, sub_outputdim=512, learning_rate=1e-4, batch_size=64,
                  dropout_rate=0.2, seed=1234, beta1=0.9, beta2=0.999, epsilon=1e-7,
@@ -223,10 +252,17 @@ class Engine:
         """
         self.set_split(train_rows, test_rows)
         hist = History()
+        n_train, seed = self.n_train, self.seed
+        perms = PermutationPrefetcher(perm_fn or (lambda e: epoch_permutation(seed, e, n_train)), int(epochs))
+        try:
+            return self._fit_epochs(hist, perms, int(epochs), patience, verbose, on_epoch_end)
+        finally:
+            perms.close()
+
+    def _fit_epochs(self, hist, perms, epochs, patience, verbose, on_epoch_end):
         best, wait = np.inf, 0
-        perm_fn = perm_fn or (lambda e: epoch_permutation(self.seed, e, self.n_train))
-        for epoch in range(int(epochs)):
-            loss, val = self.train_epoch(perm_fn(epoch))
+        for epoch in range(epochs):
+            loss, val = self.train_epoch(perms.get(epoch))
             hist.epoch_ms.append(self.lib.di_last_device_ms(self._h))
             if on_epoch_end is not None:
                 loss, val = on_epoch_end(epoch, loss, val)
