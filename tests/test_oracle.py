@@ -200,3 +200,35 @@ def test_fp32_oracle_tracks_fp64_oracle():
         _, step_b = b.train_epoch(X, Y, perm, step_b)
     ya, yb = a.forward(X)[0], b.forward(X)[0]
     assert np.max(np.abs(ya - yb) / (np.abs(yb) + 1e-3)) < 1e-3
+
+
+# ---- whole trajectory against two third-party pieces: torch autograd + scikit-learn's Adam ------------------------
+def test_trajectory_matches_autograd_plus_sklearn_adam():
+    """Ten optimiser steps of one sub-network rebuilt from parts the oracle does not contain: the loss written with
+    torch.nn.functional and differentiated by autograd, the update done by scikit-learn's ``AdamOptimizer`` -- an
+    independent implementation of the rule TensorFlow's Adam applies (``lr_t = lr sqrt(1-b2^t)/(1-b1^t)``,
+    ``w -= lr_t m / (sqrt(v) + eps)``: epsilon outside the bias correction), which is what Keras' ``Adam`` of
+    multinet.py:164 runs.  The oracle's hand-written backward pass and update must land on the same weights."""
+    from sklearn.neural_network._stochastic_optimizers import AdamOptimizer
+    import torch.nn.functional as F
+
+    rng = np.random.default_rng(5)
+    P, H, O, B, lr = 7, 6, 4, 16, 3e-3
+    net = OracleNet([P], H, O, learning_rate=lr, batch_size=B, dropout_rate=0.0, seed=9, dtype=torch.float64)
+    params = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in net.get_weights()[0]]
+    b1, b2, eps = float(np.float32(0.9)), float(np.float32(0.999)), float(np.float32(1e-7))     # Keras stores them as fp32
+    arrays = [p.detach().numpy() for p in params]                   # updated in place by scikit-learn, shared with torch
+    opt = AdamOptimizer(arrays, learning_rate_init=lr, beta_1=b1, beta_2=b2, epsilon=eps)
+    for step in range(10):
+        x = rng.gamma(1.0, 1.0, size=(B, P))
+        y = np.log1p(rng.poisson(2.0, size=(B, O))).astype(np.float64)
+        xt, yt = torch.tensor(x), torch.tensor(y)
+        W1, c1, W2, c2 = params
+        yhat = F.softplus(F.relu(xt @ W1 + c1) @ W2 + c2)
+        loss = (yt * (yt - yhat) ** 2).mean()                       # wMSE, multinet.py:36-41
+        grads = torch.autograd.grad(loss, params)
+        got = net.train_step([x], [y], step)
+        assert got == pytest.approx(float(loss), rel=1e-12)
+        opt.update_params(arrays, [g.numpy() for g in grads])
+        for k in range(4):
+            np.testing.assert_allclose(net.w[0][k].numpy(), arrays[k], rtol=1e-9, atol=1e-13)
