@@ -159,3 +159,21 @@ def test_sharded_fit_needs_a_seed():
     net = CpuMultiNet(ncores=1, sub_outputdim=8, max_epochs=1, verbose=0, seed=None, shard=ShardContext(0, 2))
     with pytest.raises(ValueError, match="seed"):
         net.fit(raw)
+
+
+@pytest.mark.parametrize("cell_subset, n_cells", [(0.5, 60), (80, 80)])
+def test_cell_subset_draws_the_cells_the_reference_draws(cell_subset, n_cells):
+    """``fit(cell_subset=...)`` (multinet.py:185-189): a fraction or a count of cells, drawn by ``DataFrame.sample`` from
+    the numpy stream seeded just before -- so the same seed picks the same cells, and everything downstream (split,
+    training) sees only them."""
+    raw = synthetic_counts(120, 60, seed=8)
+    np.random.seed(5)
+    want = raw.sample(frac=cell_subset) if cell_subset < 1 else raw.sample(cell_subset)
+    net = CpuMultiNet(ncores=1, sub_outputdim=16, max_epochs=1, seed=5, verbose=0,
+                      architecture=[{"type": "dense", "neurons": 8, "activation": "relu"}])
+    net.fit(raw, cell_subset=cell_subset, NN_lim=30, minVMR=0.0)
+    used = np.concatenate([net.train_cells, net.test_cells])
+    assert len(used) == n_cells and set(used) == set(want.index)
+    assert len(net.test_cells) == int(0.05 * n_cells)
+    out = net.predict(raw)                                   # predict is free to see every cell again
+    assert out.shape == raw.shape and np.isfinite(out.values).all()
